@@ -1,0 +1,212 @@
+/*
+ * lantern_b200 — C ABI of the B200-native LANTERN verification hot path.
+ *
+ * The reference (jadohu/LANTERN) is pure Python/PyTorch and has no FFI, plugin or operator
+ * registry; its boundary for this path is a set of Python call signatures.
+ * Each entry point below states which reference code it replaces.  The Python shims in
+ * lantern_b200/ keep those signatures and call this library through ctypes
+ * (see INTEGRATION.md for the binding a reference maintainer would add).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; all `*_dev` pointers are CUDA device pointers owned by
+ *     the caller; nothing is allocated, cached or freed inside unless the call says so;
+ *   - every launch goes to the caller's `stream` (a cudaStream_t passed as void*; NULL = legacy
+ *     default stream); calls are asynchronous unless documented otherwise;
+ *   - return value: 0 = LANTERN_OK, negative = LANTERN_E_*, positive = cudaError_t;
+ *     `lantern_last_error()` returns a thread-local message for the last failure;
+ *   - re-entrant, no global mutable state except the sessions the caller creates.
+ */
+#ifndef LANTERN_B200_H_
+#define LANTERN_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LANTERN_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define LANTERN_API __attribute__((visibility("default")))
+#else
+#define LANTERN_API
+#endif
+
+enum {
+  LANTERN_OK = 0,
+  LANTERN_E_INVALID = -1,      /* bad argument (message says which) */
+  LANTERN_E_UNSUPPORTED = -2,  /* valid but not implemented for this size / mode */
+  LANTERN_E_WORKSPACE = -3,    /* workspace too small */
+  LANTERN_E_NO_DEVICE = -4     /* no sm_100 device */
+};
+
+enum { LANTERN_F32 = 0, LANTERN_BF16 = 1, LANTERN_F16 = 2 };
+
+/* Model families: the per-family differences of evaluate_posterior. */
+enum {
+  LANTERN_FAMILY_VANILLA = 0,  /* models/drafters/utils.py:333-410 (tail row not re-warped, :408) */
+  LANTERN_FAMILY_LLAMAGEN = 1, /* models/ea_model_llamagen.py:463-669, :709-787 */
+  LANTERN_FAMILY_ANOLE = 2,    /* models/ea_model_anole.py:464-669, :709-788 (offset 4, :931 mask) */
+  LANTERN_FAMILY_LUMINA = 3    /* models/ea_model_lumina_mgpt.py:556-729 */
+};
+
+/* Lumina row classes of MultiModalLogitsProcessor (ea_model_lumina_mgpt.py:45-86). */
+enum { LANTERN_ROW_IMAGE = 0, LANTERN_ROW_NEWLINE = 1, LANTERN_ROW_EOI = 2 };
+
+/* Bits of lantern_accept_out.flags[b]. */
+enum {
+  LANTERN_OUT_RESIDUAL_TAIL = 1,    /* sample_p is the residual distribution (adjustflag path) */
+  LANTERN_OUT_UNIFORM_FALLBACK = 2  /* a residual summed to 0 and was reset to ones (:775-776) */
+};
+
+#define LANTERN_MAX_SYNTAX_TOKENS 8
+
+/*
+ * One verify step over `n_items` independent prompts.  Shapes follow the reference:
+ * T = n_rows tree nodes (root included), candidates/retrieve_indices are [n_paths, depth].
+ */
+typedef struct lantern_accept_cfg {
+  int32_t n_items;   /* B: prompts in this launch (reference: 1) */
+  int32_t n_rows;    /* T: logits rows per item */
+  int32_t n_paths;   /* L */
+  int32_t depth;     /* D */
+  int32_t vocab;     /* V: elements per logits row */
+  int32_t col0;      /* first live (image-token) column */
+  int32_t ncols;     /* live columns; everything else has probability 0 */
+  int32_t logits_dtype; /* LANTERN_F32 | LANTERN_BF16 | LANTERN_F16; arithmetic is fp32 */
+  int64_t item_stride;  /* elements between consecutive items in logits_cond / logits_uncond */
+  int64_t row_stride;   /* elements between consecutive rows (>= vocab) */
+  int32_t family;       /* LANTERN_FAMILY_* */
+  int32_t static_tree;  /* 0: q(x)=1 (EAGLE-2 dynamic tree); 1: LANTERN++ static tree with drafter q */
+  float cfg_scale;      /* used when logits_uncond != NULL: uncond + (cond - uncond) * scale */
+  float temperature;    /* HF TemperatureLogitsWarper (skipped when == 1) */
+  float top_p;          /* HF TopPLogitsWarper when 1e-8 <= top_p < 1 */
+  int32_t top_k;        /* HF TopKLogitsWarper / InterleavedTopKLogitsWarper when > 0 (ties kept) */
+  int32_t lantern;      /* relaxed acceptance on/off */
+  int32_t lantern_k;    /* neighbours aggregated (k+1 are zeroed on rejection) */
+  float lantern_delta;  /* <= 1: additive bound delta; > 1: multiplicative bound (delta-1)*p(x) */
+  float lantern_delta_m1; /* (float)(delta - 1.0) computed in double by the caller */
+  int32_t table_cols;   /* row stride of nbr_table (>= min(lantern_k + 1, N - 1)) */
+  int32_t tok_offset;   /* image_token_offset: table row = token - tok_offset, entries + tok_offset */
+  int32_t n_syntax;     /* Lumina: tokens accepted with p = 1 (ea_model_lumina_mgpt.py:654-656) */
+  int32_t syntax_tokens[LANTERN_MAX_SYNTAX_TOKENS];
+  int32_t newline_token; /* Lumina: the only finite column of a NEWLINE row (8803) */
+  int32_t eoi_token;     /* Lumina: the only finite column of an EOI row (8196) */
+  int32_t retrieve_shared; /* 1: one retrieve_indices [L,D] for all items (static tree) */
+  int32_t n_uniforms;   /* row stride of `uniforms` (>= tried candidates + 1 bonus draw) */
+  int32_t n_q_rows;     /* static: rows per item in draft_op (sum over levels of parent groups) */
+  int32_t reserved0;
+  uint64_t philox_seed; /* used when uniforms == NULL */
+  uint64_t philox_step; /* verify-step counter of the device Philox stream */
+} lantern_accept_cfg;
+
+typedef struct lantern_accept_in {
+  const void* logits_cond;      /* [B, T, V] (strides above), dtype logits_dtype */
+  const void* logits_uncond;    /* same layout, or NULL: logits_cond is already CFG-mixed */
+  const int32_t* tree_tokens;   /* [B, T] token of every tree node (tree_candidates) */
+  const int32_t* retrieve;      /* [B or 1, L, D] node index, -1 padded (retrieve_indices) */
+  const uint8_t* row_kinds;     /* [B, T] LANTERN_ROW_* or NULL (all IMAGE) */
+  const int32_t* nbr_table;     /* [N, table_cols] nearest-first codebook ids (nearest_latents) */
+  const float* uniforms;        /* [B, n_uniforms] or NULL -> device Philox stream */
+  /* static tree only (evaluate_posterior_v1 extras) */
+  const float* node_q;          /* [B, T] drafter probability of each node's token (cart_candidates_prob) */
+  const float* draft_op;        /* [B, n_q_rows, V] fp32 drafter distributions (op / original_prob) */
+  const int32_t* node_qrow;     /* [T] row of draft_op holding the node's sibling-group distribution */
+  const int32_t* sib_off;       /* [T + 1] CSR offsets into sib_idx */
+  const int32_t* sib_idx;       /* earlier siblings of each node, as indices into sib_tokens rows */
+  const int32_t* sib_tokens;    /* [B, sib_tokens_stride] tokens addressed by sib_idx (tree_candidates) */
+  int64_t sib_tokens_stride;
+} lantern_accept_in;
+
+typedef struct lantern_accept_out {
+  int32_t* accept_length;  /* [B] 0 .. D-1 */
+  int32_t* best_candidate; /* [B] row of candidates */
+  int32_t* token;          /* [B] bonus token drawn from sample_p (inverse CDF, one uniform) */
+  int32_t* path_tokens;    /* [B, D] candidates[best, :a+1], rest -1 */
+  int32_t* select_indices; /* [B, D] retrieve_indices[best, :a+1], rest -1 */
+  int32_t* n_draws;        /* [B] uniforms consumed (bonus draw included) */
+  int32_t* flags;          /* [B] LANTERN_OUT_* */
+  float* sample_p;         /* [B, V] or NULL */
+} lantern_accept_out;
+
+/* Library / ABI version: (LANTERN_ABI_VERSION << 16) | patch. */
+LANTERN_API int lantern_version(void);
+LANTERN_API const char* lantern_last_error(void);
+
+/* Scratch the fused step needs for `cfg` (per-row softmax statistics). */
+LANTERN_API size_t lantern_accept_workspace_bytes(const lantern_accept_cfg* cfg);
+
+/*
+ * The fused verify step.  Replaces, for all items at once and without host round trips:
+ *   cfg_logit_process                ea_model_llamagen.py:26-29, ea_model_lumina_mgpt.py:597
+ *   tree_decoding post-processing    ea_model_llamagen.py:930-931, ea_model_anole.py:930-932,
+ *                                    ea_model_lumina_mgpt.py:597-607 (the [L,D,V] gather is never built)
+ *   prepare_logits_processor warpers drafters/utils.py:36-52 (+ HF Temperature/TopP/TopK)
+ *   evaluate_posterior[_v1]          drafters/utils.py:371-410, ea_model_llamagen.py:597-669, :709-787,
+ *                                    ea_model_anole.py:598-669, :709-788, ea_model_lumina_mgpt.py:610-726
+ *   bonus-token draw                 ea_model_llamagen.py:976-979 (torch.multinomial -> inverse CDF)
+ */
+LANTERN_API int lantern_accept_fused(const lantern_accept_cfg* cfg, const lantern_accept_in* in,
+                         const lantern_accept_out* out, void* workspace_dev, size_t workspace_bytes,
+                         void* stream);
+
+/*
+ * Bonus-token draw from caller-supplied probability rows (update_inference_inputs given a
+ * sample_p that did not come from lantern_accept_fused): token[b] = min{i : cdf_i > u[b] * total}.
+ * Replaces torch.multinomial(prob, 1) at ea_model_llamagen.py:978, ea_model_lumina_mgpt.py:781.
+ */
+LANTERN_API int lantern_sample_tokens(const float* probs_dev, int64_t row_stride, int32_t n_rows, int32_t vocab,
+                          const float* uniforms_dev, int32_t* tokens_dev, void* stream);
+
+/*
+ * KV-cache compaction of update_inference_inputs (ea_model_llamagen.py:962-970,
+ * ea_model_lumina_mgpt.py:741-746, drafters/kv_cache.py:38-52): for every slab
+ * [n_outer, S_max, head_dim] (n_outer = 2*layers*batch*heads flattened) copy positions
+ * select[b, 0:n_keep[b]] to prev_len[b] .. prev_len[b]+n_keep[b].  `batch_of_outer` maps the flattened
+ * outer index to its item: b = (outer / outer_per_batch) % n_batch.
+ */
+typedef struct lantern_kv_cfg {
+  int32_t n_slabs;
+  int32_t elem_bytes;       /* 2 (bf16/fp16) or 4 */
+  int64_t n_outer;          /* product of the leading dims of one slab */
+  int64_t outer_per_batch;  /* heads (the dims after batch, before S) */
+  int32_t n_batch;          /* batch dim of the slab (2 for parallel CFG) */
+  int32_t s_max;            /* max_position_embeddings */
+  int32_t head_dim;
+  int32_t max_keep;         /* row stride of `select` (D) */
+} lantern_kv_cfg;
+LANTERN_API int lantern_kv_compact(const lantern_kv_cfg* cfg, void* const* slab_ptrs_dev, const int32_t* select_dev,
+                       const int32_t* prev_len_dev, const int32_t* n_keep_dev, void* stream);
+
+/*
+ * Neighbour-table build (entrypoints/generate_codebook.py:53-60): for every codebook row the ids of
+ * its K nearest other rows, nearest first; order = (squared L2 distance in fp64, id).
+ * E_dev: [N, d] fp32 row-major.  out_dev: [N, K] int32.  Synchronous workspace-free helper:
+ * allocates and frees its own scratch.
+ */
+LANTERN_API int lantern_build_neighbors(const float* E_dev, int32_t N, int32_t d, int32_t K, int32_t* out_dev,
+                            void* stream);
+
+/* Host-side copy of the device Philox stream (for tests and for seeding the CPU oracle):
+ * draw i of item `item` at step `step`, i in [0, n). */
+LANTERN_API void lantern_philox_uniforms(uint64_t seed, uint64_t step, uint32_t item, int32_t n, float* out_host);
+
+/*
+ * Host-buffer session: the call a reference-side caller makes when its logits live in host
+ * memory.  Owns device buffers, pinned staging and a stream sized for `cfg`; `lantern_session_step`
+ * copies only the live column window of the logits to the device, runs lantern_accept_fused and
+ * copies the per-item results back, synchronously.
+ */
+typedef struct lantern_session lantern_session;
+LANTERN_API int lantern_session_create(const lantern_accept_cfg* cfg, const int32_t* nbr_table_host, int32_t table_rows,
+                           lantern_session** out);
+LANTERN_API int lantern_session_step(lantern_session* s, const lantern_accept_cfg* cfg, const lantern_accept_in* in_host,
+                         const lantern_accept_out* out_host);
+LANTERN_API void lantern_session_destroy(lantern_session* s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LANTERN_B200_H_ */

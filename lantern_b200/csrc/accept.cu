@@ -1,0 +1,704 @@
+// Fused relaxed-acceptance verify step (sm_100a).
+//
+// Two phases behind one entry point (lantern_accept_fused):
+//
+//   row_stats_kernel  — HBM-bound.  One CTA per logits row (persistent grid over B*T rows): streams the
+//                       cond/uncond rows once with 128-bit loads, applies the CFG mix and temperature,
+//                       finds the top-k threshold (exact k-th largest, ties kept) and the softmax max / sum
+//                       over the kept columns.  Only 32 bytes per row go back to HBM.
+//   walk_kernel       — one CTA per prompt.  Literal restatement of evaluate_posterior[_v1]: the level
+//                       loop, candidate dedup, latent-proximity relaxation (neighbour-table gather from the
+//                       shared-memory probability vector, fp64 warp-shuffle scan, threshold search),
+//                       accept test against the supplied / Philox uniform, residual bookkeeping, tail
+//                       distribution and the bonus-token inverse-CDF draw.  The [L,D,V] gather of
+//                       tree_decoding is never materialised: rows are addressed through retrieve_indices.
+//
+// Reference semantics: SURVEY.md Appendix A; file:line citations are in include/lantern_b200.h.
+#include <algorithm>
+#include <cstdio>
+
+#include "common.cuh"
+
+namespace lantern {
+
+struct RowStats {
+  float thr;   // top-k threshold on the tempered value (keep s >= thr); -inf = keep all
+  float mx;    // max of the tempered row
+  float sum;   // sum over kept columns of exp(s - mx)
+  float vcut;  // top-p: columns with (s, idx) <= (vcut, icut) are removed; -inf / -1 = none
+  int icut;
+  int kind;    // LANTERN_ROW_*
+  int pad0, pad1;
+};
+static_assert(sizeof(RowStats) == 32, "RowStats layout");
+
+struct AcceptParams {
+  lantern_accept_cfg cfg;
+  lantern_accept_in in;
+  lantern_accept_out out;
+  RowStats* stats;
+  MixParams mix;
+  int vec_ok;     // rows can be read with 4-element vector loads
+  int do_topk;    // 0 < top_k < ncols
+  int do_topp;
+  int tail_raw;   // vanilla: tail row softmax without the processors
+  int lumina;
+  int static_zero_q;  // static + relaxed rejection zeroes neighbours in q (LlamaGen/Anole) instead of gtp
+};
+
+constexpr int kStatThreads = 512;
+constexpr int kWalkThreads = 512;
+constexpr int kMaxSib = 64;
+
+__device__ __forceinline__ bool kept_col(float s, int idx, const RowStats& st) {
+  return (s >= st.thr) && ((s > st.vcut) || (s == st.vcut && idx > st.icut));
+}
+
+// ----------------------------------------------------------------------------------------------
+// Exact k-th largest of the block's register-resident keys: MSB-first radix select, 8 bits per pass,
+// shared-memory histograms.  Returns the key K with count(key > K) < k <= count(key >= K).
+// ----------------------------------------------------------------------------------------------
+template <int NE>
+__device__ __forceinline__ uint32_t radix_select_kth(const float (&s)[NE], int k, unsigned* hist /*[258]*/) {
+  uint32_t prefix = 0, mask = 0;
+  int krem = k;
+  const int tid = threadIdx.x;
+#pragma unroll 1
+  for (int shift = 24; shift >= 0; shift -= 8) {
+    for (int i = tid; i < 256; i += blockDim.x) hist[i] = 0;
+    __syncthreads();
+#pragma unroll
+    for (int e = 0; e < NE; ++e) {
+      const uint32_t key = float_key(s[e]);
+      if ((key & mask) == prefix) atomicAdd(&hist[(key >> shift) & 0xffu], 1u);
+    }
+    __syncthreads();
+    if (tid < 32) {
+      // lane l owns bins [8l, 8l+8); count everything in higher lanes, then walk own bins downwards
+      unsigned c[8], tot = 0;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { c[j] = hist[tid * 8 + j]; tot += c[j]; }
+      unsigned above = 0;
+      for (int l = 31; l > 0; --l) {
+        const unsigned t = __shfl_sync(0xffffffffu, tot, l);
+        if (tid < l) above += t;
+      }
+      unsigned run = above;
+#pragma unroll
+      for (int j = 7; j >= 0; --j) {
+        if (run < (unsigned)krem && run + c[j] >= (unsigned)krem) {
+          hist[256] = tid * 8 + j;   // selected digit
+          hist[257] = run;           // keys strictly above it (within the current prefix)
+        }
+        run += c[j];
+      }
+    }
+    __syncthreads();
+    prefix |= hist[256] << shift;
+    mask |= 0xffu << shift;
+    krem -= (int)hist[257];
+    __syncthreads();
+  }
+  return prefix;
+}
+
+// ----------------------------------------------------------------------------------------------
+// Phase 1: per-row statistics
+// ----------------------------------------------------------------------------------------------
+template <int DT, int NQ, bool VEC>
+__global__ void __launch_bounds__(kStatThreads) row_stats_kernel(const AcceptParams P) {
+  constexpr int NE = NQ * 4;
+  __shared__ unsigned hist[258];
+  __shared__ float fscratch[33];
+  __shared__ double dscratch[33];
+
+  const lantern_accept_cfg& cfg = P.cfg;
+  const int tid = threadIdx.x;
+  const long long n_rows_total = (long long)cfg.n_items * cfg.n_rows;
+
+  for (long long row = blockIdx.x; row < n_rows_total; row += gridDim.x) {
+    const int b = (int)(row / cfg.n_rows), t = (int)(row % cfg.n_rows);
+    RowStats st;
+    st.thr = -INFINITY; st.mx = 0.f; st.sum = 1.f; st.vcut = -INFINITY; st.icut = -1;
+    st.kind = P.in.row_kinds ? (int)P.in.row_kinds[row] : LANTERN_ROW_IMAGE;
+    st.pad0 = st.pad1 = 0;
+    if (st.kind != LANTERN_ROW_IMAGE) {   // one-hot rows: nothing to read
+      if (tid == 0) P.stats[row] = st;
+      continue;
+    }
+    const int64_t base = (int64_t)b * cfg.item_stride + (int64_t)t * cfg.row_stride + cfg.col0;
+    float s[NE];
+    // ---- stream the row: all loads are issued before any use ----
+    {
+      float c4[NQ][4], u4[NQ][4];
+#pragma unroll
+      for (int q = 0; q < NQ; ++q) {
+        const int e0 = (q * kStatThreads + tid) * 4;
+        if (VEC) {
+          if (e0 < cfg.ncols) {
+            Elem<DT>::load4(P.in.logits_cond, base + e0, c4[q]);
+            if (P.mix.has_uncond) Elem<DT>::load4(P.in.logits_uncond, base + e0, u4[q]);
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            if (e0 + j < cfg.ncols) {
+              c4[q][j] = Elem<DT>::load1(P.in.logits_cond, base + e0 + j);
+              if (P.mix.has_uncond) u4[q][j] = Elem<DT>::load1(P.in.logits_uncond, base + e0 + j);
+            }
+          }
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < NQ; ++q) {
+        const int e0 = (q * kStatThreads + tid) * 4;
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          s[q * 4 + j] = (e0 + j < cfg.ncols) ? mix_temper(c4[q][j], P.mix.has_uncond ? u4[q][j] : 0.f, P.mix)
+                                               : -INFINITY;
+      }
+    }
+    // ---- top-k threshold ----
+    if (P.do_topk) st.thr = key_float(radix_select_kth<NE>(s, cfg.top_k, hist));   // padded slots are -inf
+    // ---- softmax statistics over the kept columns ----
+    float m = -INFINITY;
+#pragma unroll
+    for (int e = 0; e < NE; ++e) m = fmaxf(m, s[e]);
+    m = block_reduce(m, OpMaxF(), -INFINITY, fscratch);
+    float part = 0.f;
+#pragma unroll
+    for (int e = 0; e < NE; ++e) {
+      if (s[e] >= st.thr) part += expf(s[e] - m);   // padded slots are -inf -> exp = 0
+    }
+    const double tot = block_reduce((double)part, OpSum(), 0.0, dscratch);
+    st.mx = m;
+    st.sum = (float)tot;
+    if (tid == 0) P.stats[row] = st;
+  }
+}
+
+// ----------------------------------------------------------------------------------------------
+// Phase 2: the acceptance walk, one CTA per prompt
+// ----------------------------------------------------------------------------------------------
+struct WalkSmem {
+  float* p;          // [ncols] probability window (gtp)
+  unsigned* nbmask;  // [ceil(ncols/32)] neighbour bitmap (static LlamaGen/Anole rejection)
+  int* ri;           // [L*D]
+  int* tok;          // [T]
+  int* tried;        // [L]
+  int* sib;          // [kMaxSib] tokens of the rejected node's earlier siblings
+  unsigned char* eq; // [L]
+  double* dscr;      // [34]
+  float* fscr;       // [34]
+  int* iscr;         // [40]
+};
+
+template <int DT, bool VEC>
+__device__ __forceinline__ void load_probs(const AcceptParams& P, int b, int node, const RowStats& st, float* p,
+                                           bool raw) {
+  const lantern_accept_cfg& cfg = P.cfg;
+  const int64_t base = (int64_t)b * cfg.item_stride + (int64_t)node * cfg.row_stride + cfg.col0;
+  MixParams mix = P.mix;
+  if (raw) mix.do_temp = 0;
+  const float inv = __fdiv_rn(1.0f, st.sum);
+  const int nquads = (cfg.ncols + 3) >> 2;
+  for (int g = threadIdx.x; g < nquads; g += blockDim.x) {
+    const int e0 = g * 4;
+    float c4[4], u4[4] = {0.f, 0.f, 0.f, 0.f};
+    if (VEC) {
+      Elem<DT>::load4(P.in.logits_cond, base + e0, c4);
+      if (mix.has_uncond) Elem<DT>::load4(P.in.logits_uncond, base + e0, u4);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (e0 + j < cfg.ncols) {
+          c4[j] = Elem<DT>::load1(P.in.logits_cond, base + e0 + j);
+          if (mix.has_uncond) u4[j] = Elem<DT>::load1(P.in.logits_uncond, base + e0 + j);
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (e0 + j < cfg.ncols) {
+        const float s = mix_temper(c4[j], u4[j], mix);
+        float v = 0.f;
+        if (raw || kept_col(s, e0 + j, st)) v = __fmul_rn(expf(s - st.mx), inv);
+        p[e0 + j] = v;
+      }
+    }
+  }
+}
+
+// raw softmax statistics of one row (vanilla tail row, drafters/utils.py:408-409)
+template <int DT, bool VEC>
+__device__ __forceinline__ RowStats raw_row_stats(const AcceptParams& P, int b, int node, float* fscr, double* dscr) {
+  const lantern_accept_cfg& cfg = P.cfg;
+  const int64_t base = (int64_t)b * cfg.item_stride + (int64_t)node * cfg.row_stride + cfg.col0;
+  MixParams mix = P.mix;
+  mix.do_temp = 0;
+  float m = -INFINITY;
+  for (int e = threadIdx.x; e < cfg.ncols; e += blockDim.x) {
+    const float c = Elem<DT>::load1(P.in.logits_cond, base + e);
+    const float u = mix.has_uncond ? Elem<DT>::load1(P.in.logits_uncond, base + e) : 0.f;
+    m = fmaxf(m, mix_temper(c, u, mix));
+  }
+  m = block_reduce(m, OpMaxF(), -INFINITY, fscr);
+  float part = 0.f;
+  for (int e = threadIdx.x; e < cfg.ncols; e += blockDim.x) {
+    const float c = Elem<DT>::load1(P.in.logits_cond, base + e);
+    const float u = mix.has_uncond ? Elem<DT>::load1(P.in.logits_uncond, base + e) : 0.f;
+    part += expf(mix_temper(c, u, mix) - m);
+  }
+  const double tot = block_reduce((double)part, OpSum(), 0.0, dscr);
+  RowStats st;
+  st.thr = -INFINITY; st.mx = m; st.sum = (float)tot; st.vcut = -INFINITY; st.icut = -1;
+  st.kind = LANTERN_ROW_IMAGE; st.pad0 = st.pad1 = 0;
+  return st;
+}
+
+template <int DT, bool VEC>
+__global__ void __launch_bounds__(kWalkThreads) walk_kernel(const AcceptParams P) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const lantern_accept_cfg& cfg = P.cfg;
+  const int b = blockIdx.x, tid = threadIdx.x, NT = blockDim.x;
+  const int L = cfg.n_paths, D = cfg.depth, T = cfg.n_rows, V = cfg.vocab;
+  const int ncols = cfg.ncols, col0 = cfg.col0, col1 = cfg.col0 + cfg.ncols;
+  const int off = cfg.tok_offset;
+
+  // ---- carve shared memory ----
+  WalkSmem S;
+  size_t o = 0;
+  S.p = reinterpret_cast<float*>(smem_raw + o);            o += (size_t)((ncols + 3) & ~3) * 4;
+  S.nbmask = reinterpret_cast<unsigned*>(smem_raw + o);     o += (size_t)(((ncols + 31) >> 5) + 3 & ~3) * 4;
+  S.dscr = reinterpret_cast<double*>(smem_raw + o);         o += 34 * 8;
+  S.ri = reinterpret_cast<int*>(smem_raw + o);              o += (size_t)((L * D + 3) & ~3) * 4;
+  S.tok = reinterpret_cast<int*>(smem_raw + o);             o += (size_t)((T + 3) & ~3) * 4;
+  S.tried = reinterpret_cast<int*>(smem_raw + o);           o += (size_t)((L + 3) & ~3) * 4;
+  S.sib = reinterpret_cast<int*>(smem_raw + o);             o += kMaxSib * 4;
+  S.fscr = reinterpret_cast<float*>(smem_raw + o);          o += 36 * 4;
+  S.iscr = reinterpret_cast<int*>(smem_raw + o);            o += 40 * 4;
+  S.eq = smem_raw + o;
+
+  const int* ri_g = P.in.retrieve + (cfg.retrieve_shared ? 0 : (size_t)b * L * D);
+  const int* tok_g = P.in.tree_tokens + (size_t)b * T;
+  for (int i = tid; i < L * D; i += NT) S.ri[i] = ri_g[i];
+  for (int i = tid; i < T; i += NT) S.tok[i] = tok_g[i];
+  __syncthreads();
+  auto cand = [&](int j, int i) -> int {
+    const int n = S.ri[j * D + i];
+    return n >= 0 ? S.tok[n] : -1;
+  };
+  for (int j = tid; j < L; j += NT) S.eq[j] = (cand(j, 0) == cand(0, 0)) ? 1 : 0;
+  __syncthreads();
+
+  // ---- distribution state: window S.p + one explicit out-of-window token + uniform remainder ----
+  int extra_tok = -1;
+  float p_extra = 0.f, p_out = 0.f;
+  auto prob_of = [&](int tkn) -> float {
+    if (tkn >= col0 && tkn < col1) return S.p[tkn - col0];
+    if (tkn == extra_tok) return p_extra;
+    return p_out;
+  };
+  auto set_distribution = [&](int node, bool raw) {
+    const long long row = (long long)b * T + node;
+    RowStats st = P.stats[row];
+    __syncthreads();
+    extra_tok = -1; p_extra = 0.f; p_out = 0.f;
+    if (st.kind != LANTERN_ROW_IMAGE) {
+      for (int e = tid; e < ncols; e += NT) S.p[e] = 0.f;
+      extra_tok = st.kind == LANTERN_ROW_NEWLINE ? cfg.newline_token : cfg.eoi_token;
+      p_extra = 1.0f;
+      if (extra_tok >= col0 && extra_tok < col1) {   // degenerate configs: keep it inside the window
+        __syncthreads();
+        if (tid == 0) S.p[extra_tok - col0] = 1.0f;
+        extra_tok = -1; p_extra = 0.f;
+      }
+    } else {
+      if (raw) st = raw_row_stats<DT, VEC>(P, b, node, S.fscr, S.dscr);
+      load_probs<DT, VEC>(P, b, node, st, S.p, raw);
+    }
+    __syncthreads();
+  };
+  auto uniform = [&](int d) -> float {
+    if (P.in.uniforms) return P.in.uniforms[(size_t)b * cfg.n_uniforms + d];
+    return philox_uniform(cfg.philox_seed, cfg.philox_step, (uint32_t)b, (uint32_t)d);
+  };
+  auto is_syntax = [&](int tkn) -> bool {
+    for (int i = 0; i < cfg.n_syntax; ++i)
+      if (cfg.syntax_tokens[i] == tkn) return true;
+    return false;
+  };
+
+  int accept_length = 1, best = 0, draws = 0, out_flags = 0;
+  bool adjust = false;
+  const int kk = cfg.lantern ? min(cfg.lantern_k, cfg.table_cols) : 0;
+  const int kk1 = cfg.lantern ? min(cfg.lantern_k + 1, cfg.table_cols) : 0;
+
+  for (int lvl = 1; lvl < D; ++lvl) {
+    if (lvl != accept_length) break;
+    adjust = false;
+    // fi = first row still matching the accepted prefix
+    int fi = L;
+    for (int j = tid; j < L; j += NT)
+      if (S.eq[j]) { fi = j; break; }
+    fi = block_reduce(fi, OpMinI(), L, S.iscr);
+    int node = S.ri[fi * D + lvl - 1];
+    if (node < 0) node += T;
+    set_distribution(node, false);
+
+    int ntried = 0;
+    bool accepted = false;
+    for (int j = 0; j < L && !accepted; ++j) {
+      if (!S.eq[j]) continue;
+      const int cnode = S.ri[j * D + lvl];
+      const int x = cnode >= 0 ? S.tok[cnode] : -1;
+      if (x == -1) continue;
+      bool dup = false;
+      for (int q = 0; q < ntried; ++q) dup |= (S.tried[q] == x);
+      if (dup) continue;
+      __syncthreads();
+      if (tid == 0) S.tried[ntried] = x;
+      ++ntried;
+      __syncthreads();
+
+      const float r = uniform(draws++);
+      float px = prob_of(x);
+      bool relaxable = true;
+      if (P.lumina) {
+        if (is_syntax(x)) { px = 1.0f; relaxable = false; }
+        else if (!(x >= col0 && x < col1)) { px = 0.0f; relaxable = false; }
+      }
+      int idx = -1;
+      const int* nb_row = nullptr;
+      if (cfg.lantern && relaxable) {
+        nb_row = P.in.nbr_table + (size_t)(x - off) * cfg.table_cols;
+        const float bound = cfg.lantern_delta > 1.0f ? __fmul_rn(cfg.lantern_delta_m1, px) : cfg.lantern_delta;
+        double carry = 0.0;
+        int n_ok = 0;
+        for (int base_t = 0; base_t < kk; base_t += NT) {
+          const int tt = base_t + tid;
+          double v = 0.0;
+          if (tt < kk) v = (double)prob_of(__ldg(nb_row + tt) + off);
+          double total;
+          const double incl = carry + block_scan_incl(v, S.dscr, &total);
+          const float cs = (float)incl;
+          const bool ok = (tt < kk) && (cs <= bound);
+          const int chunk = min(NT, kk - base_t);
+          const int cnt = block_reduce(ok ? 1 : 0, OpSum(), 0, S.iscr);
+          if (cnt > 0 && tid == cnt - 1) S.fscr[35] = cs;   // cumsum at the last index within the bound
+          n_ok += cnt;
+          carry += total;
+          if (cnt < chunk) break;
+        }
+        __syncthreads();
+        if (n_ok > 0) {
+          idx = n_ok - 1;
+          px = __fadd_rn(px, S.fscr[35]);
+        }
+      }
+      float qx = 1.0f;
+      if (cfg.static_tree) {
+        qx = P.in.node_q[(size_t)b * T + cnode];
+        if (qx <= 0.f) continue;
+      }
+      const float acp = __fdiv_rn(px, qx);
+      if (r <= acp) {
+        __syncthreads();
+        for (int jj = tid; jj < L; jj += NT)
+          if (S.eq[jj] && cand(jj, lvl) != x) S.eq[jj] = 0;
+        ++accept_length;
+        best = j;
+        accepted = true;
+        __syncthreads();
+        break;
+      }
+      // ---------------- rejection: residual distribution ----------------
+      const bool zero_nb = cfg.lantern && relaxable && idx != -1;
+      if (cfg.static_tree) {
+        const float* q = P.in.draft_op + ((size_t)b * cfg.n_q_rows + P.in.node_qrow[cnode]) * (size_t)V;
+        const int s0 = P.in.sib_off[cnode], s1 = min(P.in.sib_off[cnode + 1], s0 + kMaxSib);
+        const int* sib_tok = P.in.sib_tokens + (size_t)b * P.in.sib_tokens_stride;
+        __syncthreads();
+        for (int s = s0 + tid; s < s1; s += NT) S.sib[s - s0] = sib_tok[P.in.sib_idx[s]];
+        __syncthreads();
+        const int nsib = s1 - s0;
+        auto is_sib = [&](int tkn) -> bool {
+          bool hit = false;
+          for (int s = 0; s < nsib; ++s) hit |= (S.sib[s] == tkn);
+          return hit;
+        };
+        float qsum = 1.0f;
+        if (s1 > s0) {   // q[earlier siblings] = 0; q /= q.sum()
+          double part = 0.0;
+          for (int v = tid; v < V; v += NT) part += is_sib(v) ? 0.0 : (double)q[v];
+          qsum = (float)block_reduce(part, OpSum(), 0.0, S.dscr);
+        }
+        if (zero_nb) {
+          if (P.static_zero_q) {
+            for (int w = tid; w < ((ncols + 31) >> 5); w += NT) S.nbmask[w] = 0u;
+            __syncthreads();
+            for (int tt = tid; tt < kk1; tt += NT) {
+              const int nbt = __ldg(nb_row + tt) + off - col0;
+              if (nbt >= 0 && nbt < ncols) atomicOr(&S.nbmask[nbt >> 5], 1u << (nbt & 31));
+            }
+          } else {
+            for (int tt = tid; tt < kk1; tt += NT) {
+              const int nbt = __ldg(nb_row + tt) + off - col0;
+              if (nbt >= 0 && nbt < ncols) S.p[nbt] = 0.f;
+            }
+          }
+        }
+        __syncthreads();
+        const bool use_mask = zero_nb && P.static_zero_q;
+        for (int e = tid; e < ncols; e += NT) {
+          const int tkn = e + col0;
+          float qv = is_sib(tkn) ? 0.f : q[tkn];
+          if (s1 > s0) qv = __fdiv_rn(qv, qsum);
+          if (use_mask && ((S.nbmask[e >> 5] >> (e & 31)) & 1u)) qv = 0.f;
+          S.p[e] = fmaxf(__fsub_rn(S.p[e], qv), 0.f);
+        }
+        if (extra_tok >= 0) {
+          float qv = is_sib(extra_tok) ? 0.f : q[extra_tok];
+          if (s1 > s0) qv = __fdiv_rn(qv, qsum);
+          p_extra = fmaxf(__fsub_rn(p_extra, qv), 0.f);
+        }
+      } else {
+        if (zero_nb) {
+          for (int tt = tid; tt < kk1; tt += NT) {
+            const int nbt = __ldg(nb_row + tt) + off - col0;
+            if (nbt >= 0 && nbt < ncols) S.p[nbt] = 0.f;
+          }
+        }
+        if (x >= col0 && x < col1) { if (tid == 0) S.p[x - col0] = 0.f; }
+        else if (x == extra_tok) p_extra = 0.f;
+      }
+      __syncthreads();
+      double part = 0.0;
+      for (int e = tid; e < ncols; e += NT) part += (double)S.p[e];
+      double tot = block_reduce(part, OpSum(), 0.0, S.dscr);
+      tot += (double)p_extra + (double)p_out * (double)(V - ncols - (extra_tok >= 0 ? 1 : 0));
+      float ssum = (float)tot;
+      if (ssum == 0.f) {   // gtp = ones_like(gtp)
+        for (int e = tid; e < ncols; e += NT) S.p[e] = 1.0f;
+        if (extra_tok >= 0) p_extra = 1.0f;
+        p_out = 1.0f;
+        ssum = (float)V;
+        out_flags |= LANTERN_OUT_UNIFORM_FALLBACK;
+        __syncthreads();
+      }
+      for (int e = tid; e < ncols; e += NT) S.p[e] = __fdiv_rn(S.p[e], ssum);
+      p_extra = __fdiv_rn(p_extra, ssum);
+      p_out = __fdiv_rn(p_out, ssum);
+      adjust = true;
+      __syncthreads();
+    }
+  }
+
+  // ---------------- tail distribution ----------------
+  const bool residual_tail = adjust && (accept_length != D);
+  if (residual_tail) {
+    out_flags |= LANTERN_OUT_RESIDUAL_TAIL;
+  } else {
+    int node = S.ri[best * D + accept_length - 1];
+    if (node < 0) node += T;
+    set_distribution(node, P.tail_raw != 0);
+  }
+  __syncthreads();
+
+  // ---------------- bonus token: inverse CDF, fp64, index order ----------------
+  const float u = uniform(draws++);
+  const int per = (ncols + NT - 1) / NT;
+  const int i0 = min(tid * per, ncols), i1 = min(i0 + per, ncols);
+  double loc = 0.0;
+  for (int i = i0; i < i1; ++i) loc += (double)S.p[i];
+  double wtot;
+  const double incl = block_scan_incl(loc, S.dscr, &wtot);
+  const double massA = (double)p_out * (double)col0;
+  const int n_suffix_uniform = V - col1 - ((extra_tok >= col1) ? 1 : 0);
+  const double massB = (double)p_extra + (double)p_out * (double)n_suffix_uniform;
+  const double total = massA + wtot + massB;
+  const double target = (double)u * total;
+  __syncthreads();
+  if (tid == 0) { S.iscr[36] = 0x7fffffff; S.iscr[37] = -1; }
+  __syncthreads();
+  {
+    double run = massA + incl - loc;
+    if (target >= run && target < run + loc) {
+      for (int i = i0; i < i1; ++i) {
+        run += (double)S.p[i];
+        if (run > target) { atomicMin(&S.iscr[36], i + col0); break; }
+      }
+    }
+    int last_nz = -1;
+    for (int i = i0; i < i1; ++i) if (S.p[i] > 0.f) last_nz = i + col0;
+    if (last_nz >= 0) atomicMax(&S.iscr[37], last_nz);
+  }
+  __syncthreads();
+  int token = S.iscr[36];
+  if (token == 0x7fffffff) {
+    if (target < massA && p_out > 0.f) {
+      token = min(col0 - 1, (int)(target / (double)p_out));
+    } else {
+      const double rem = target - massA - wtot;
+      if (p_out > 0.f && rem >= 0.0) {
+        token = min(V - 1, col1 + (int)(rem / (double)p_out));
+      } else if (p_extra > 0.f) {
+        token = extra_tok;
+      } else {
+        token = S.iscr[37] >= 0 ? S.iscr[37] : col0;   // numerical fall-through: last non-zero entry
+      }
+    }
+  }
+
+  // ---------------- outputs ----------------
+  const int a = accept_length - 1;
+  if (tid == 0) {
+    P.out.accept_length[b] = a;
+    P.out.best_candidate[b] = best;
+    P.out.token[b] = token;
+    if (P.out.n_draws) P.out.n_draws[b] = draws;
+    if (P.out.flags) P.out.flags[b] = out_flags;
+  }
+  for (int i = tid; i < D; i += NT) {
+    if (P.out.path_tokens) P.out.path_tokens[(size_t)b * D + i] = i <= a ? cand(best, i) : -1;
+    if (P.out.select_indices) P.out.select_indices[(size_t)b * D + i] = i <= a ? S.ri[best * D + i] : -1;
+  }
+  if (P.out.sample_p) {
+    float* sp = P.out.sample_p + (size_t)b * V;
+    for (int v = tid; v < V; v += NT) sp[v] = prob_of(v);
+  }
+}
+
+// ----------------------------------------------------------------------------------------------
+// Host side
+// ----------------------------------------------------------------------------------------------
+static size_t walk_smem_bytes(const lantern_accept_cfg& c) {
+  size_t o = 0;
+  o += (size_t)((c.ncols + 3) & ~3) * 4;
+  o += (size_t)((((c.ncols + 31) >> 5) + 3) & ~3) * 4;
+  o += 34 * 8;
+  o += (size_t)((c.n_paths * c.depth + 3) & ~3) * 4;
+  o += (size_t)((c.n_rows + 3) & ~3) * 4;
+  o += (size_t)((c.n_paths + 3) & ~3) * 4;
+  o += kMaxSib * 4 + 36 * 4 + 40 * 4;
+  o += (size_t)((c.n_paths + 15) & ~15);
+  return o;
+}
+
+template <int DT, bool VEC>
+static int launch_all(const AcceptParams& P, cudaStream_t stream) {
+  const lantern_accept_cfg& c = P.cfg;
+  const long long rows = (long long)c.n_items * c.n_rows;
+  const int nquads = (c.ncols + 3) / 4;
+  const int nq = (nquads + kStatThreads - 1) / kStatThreads;
+  const int grid = (int)std::min<long long>(rows, (long long)kNumSMs * 4);
+#define LAUNCH_STATS(NQ) row_stats_kernel<DT, NQ, VEC><<<grid, kStatThreads, 0, stream>>>(P)
+  if (nq <= 1) LAUNCH_STATS(1);
+  else if (nq <= 2) LAUNCH_STATS(2);
+  else if (nq <= 4) LAUNCH_STATS(4);
+  else if (nq <= 8) LAUNCH_STATS(8);
+  else if (nq <= 16) LAUNCH_STATS(16);
+  else {
+    set_error("ncols=%d exceeds the register-resident row limit (%d)", c.ncols, 16 * 4 * kStatThreads);
+    return LANTERN_E_UNSUPPORTED;
+  }
+#undef LAUNCH_STATS
+  LANTERN_CUDA(cudaGetLastError());
+  const size_t smem = walk_smem_bytes(c);
+  if (smem > 227 * 1024) {
+    set_error("walk kernel needs %zu bytes of shared memory (> 227 KB): ncols too large", smem);
+    return LANTERN_E_UNSUPPORTED;
+  }
+  auto kern = walk_kernel<DT, VEC>;
+  if (smem > 48 * 1024)
+    LANTERN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  kern<<<c.n_items, kWalkThreads, smem, stream>>>(P);
+  LANTERN_CUDA(cudaGetLastError());
+  return LANTERN_OK;
+}
+
+}  // namespace lantern
+
+using namespace lantern;
+
+extern "C" size_t lantern_accept_workspace_bytes(const lantern_accept_cfg* cfg) {
+  if (!cfg) return 0;
+  return (size_t)cfg->n_items * (size_t)cfg->n_rows * sizeof(RowStats);
+}
+
+static int validate(const lantern_accept_cfg& c, const lantern_accept_in& in, const lantern_accept_out& out) {
+#define REQUIRE(cond, msg)                 \
+  if (!(cond)) {                           \
+    set_error("lantern_accept_fused: " msg); \
+    return LANTERN_E_INVALID;              \
+  }
+  REQUIRE(c.n_items > 0 && c.n_rows > 0 && c.n_paths > 0 && c.depth > 0, "n_items/n_rows/n_paths/depth must be > 0");
+  REQUIRE(c.vocab > 0 && c.ncols > 0 && c.col0 >= 0 && c.col0 + c.ncols <= c.vocab, "bad column window");
+  REQUIRE(c.row_stride >= c.ncols && c.item_stride >= 0, "bad strides");
+  REQUIRE(c.logits_dtype >= LANTERN_F32 && c.logits_dtype <= LANTERN_F16, "bad logits_dtype");
+  REQUIRE(c.family >= LANTERN_FAMILY_VANILLA && c.family <= LANTERN_FAMILY_LUMINA, "bad family");
+  REQUIRE(in.logits_cond && in.tree_tokens && in.retrieve, "logits_cond/tree_tokens/retrieve are required");
+  REQUIRE(out.accept_length && out.best_candidate && out.token, "accept_length/best_candidate/token outputs are required");
+  REQUIRE(c.temperature > 1e-5f, "temperature must be > 1e-5 (greedy decoding has no sampling walk)");
+  REQUIRE(c.n_syntax >= 0 && c.n_syntax <= LANTERN_MAX_SYNTAX_TOKENS, "too many syntax tokens");
+  if (c.lantern) {
+    REQUIRE(in.nbr_table != nullptr, "lantern=1 needs nbr_table");
+    REQUIRE(c.lantern_k >= 1 && c.lantern_k <= c.table_cols, "lantern_k must be in [1, table_cols]");
+  }
+  if (c.static_tree) {
+    REQUIRE(in.node_q && in.draft_op && in.node_qrow && in.sib_off && in.sib_idx && in.sib_tokens,
+            "static_tree=1 needs node_q/draft_op/node_qrow/sib_off/sib_idx/sib_tokens");
+    REQUIRE(c.n_q_rows > 0, "static_tree=1 needs n_q_rows");
+  }
+  if (in.uniforms) REQUIRE(c.n_uniforms >= 1, "n_uniforms must be >= 1");
+#undef REQUIRE
+  return LANTERN_OK;
+}
+
+extern "C" int lantern_accept_fused(const lantern_accept_cfg* cfg, const lantern_accept_in* in,
+                                    const lantern_accept_out* out, void* workspace_dev, size_t workspace_bytes,
+                                    void* stream) {
+  if (!cfg || !in || !out) {
+    set_error("lantern_accept_fused: null argument");
+    return LANTERN_E_INVALID;
+  }
+  int rc = validate(*cfg, *in, *out);
+  if (rc) return rc;
+  if (1e-8f <= cfg->top_p && cfg->top_p < 1.0f) {
+    set_error("lantern_accept_fused: top_p < 1 is not implemented in the fused kernel yet");
+    return LANTERN_E_UNSUPPORTED;
+  }
+  if (!workspace_dev || workspace_bytes < lantern_accept_workspace_bytes(cfg)) {
+    set_error("lantern_accept_fused: workspace too small (%zu < %zu)", workspace_bytes,
+              lantern_accept_workspace_bytes(cfg));
+    return LANTERN_E_WORKSPACE;
+  }
+  AcceptParams P;
+  P.cfg = *cfg;
+  P.in = *in;
+  P.out = *out;
+  P.stats = static_cast<RowStats*>(workspace_dev);
+  P.mix.cfg_scale = cfg->cfg_scale;
+  P.mix.temperature = cfg->temperature;
+  P.mix.has_uncond = in->logits_uncond != nullptr;
+  P.mix.do_temp = cfg->temperature != 1.0f;
+  P.do_topk = cfg->top_k > 0 && cfg->top_k < cfg->ncols;
+  P.do_topp = 0;
+  P.tail_raw = cfg->family == LANTERN_FAMILY_VANILLA;
+  P.lumina = cfg->family == LANTERN_FAMILY_LUMINA;
+  P.static_zero_q = cfg->static_tree && cfg->family != LANTERN_FAMILY_LUMINA;
+  const int eb = cfg->logits_dtype == LANTERN_F32 ? 4 : 2;
+  const uintptr_t align = eb == 4 ? 16 : 8;
+  auto aligned = [&](const void* p) { return p == nullptr || (reinterpret_cast<uintptr_t>(p) % align) == 0; };
+  P.vec_ok = (cfg->col0 % 4 == 0) && (cfg->ncols % 4 == 0) && (cfg->row_stride % 4 == 0) &&
+             (cfg->item_stride % 4 == 0) && aligned(in->logits_cond) && aligned(in->logits_uncond);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+#define DISPATCH(DT)                                        \
+  return P.vec_ok ? launch_all<DT, true>(P, s) : launch_all<DT, false>(P, s)
+  switch (cfg->logits_dtype) {
+    case LANTERN_F32: DISPATCH(LANTERN_F32);
+    case LANTERN_BF16: DISPATCH(LANTERN_BF16);
+    default: DISPATCH(LANTERN_F16);
+  }
+#undef DISPATCH
+}

@@ -1,0 +1,192 @@
+// Shared device/host helpers for the lantern_b200 kernels (sm_100a only).
+#pragma once
+
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/lantern_b200.h"
+
+namespace lantern {
+
+void set_error(const char* fmt, ...);
+int cuda_fail(cudaError_t e, const char* what);
+
+#define LANTERN_CUDA(expr)                                        \
+  do {                                                            \
+    cudaError_t _e = (expr);                                      \
+    if (_e != cudaSuccess) return ::lantern::cuda_fail(_e, #expr); \
+  } while (0)
+
+constexpr int kWarp = 32;
+constexpr int kNumSMs = 148;  // B200
+
+// ----------------------------------------------------------------------------------------------
+// Streaming 4-element loads of a logits row (128-bit for fp32, 64-bit for bf16/fp16), L1 bypassed:
+// each row is consumed once per kernel.
+// ----------------------------------------------------------------------------------------------
+template <int DT>
+struct Elem;
+template <>
+struct Elem<LANTERN_F32> {
+  static constexpr int kBytes = 4;
+  static __device__ __forceinline__ void load4(const void* base, int64_t off, float (&o)[4]) {
+    const float4* p = reinterpret_cast<const float4*>(static_cast<const float*>(base) + off);
+    float4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+                 : "l"(p));
+    o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w;
+  }
+  static __device__ __forceinline__ float load1(const void* base, int64_t off) {
+    return __ldg(static_cast<const float*>(base) + off);
+  }
+};
+template <>
+struct Elem<LANTERN_BF16> {
+  static constexpr int kBytes = 2;
+  static __device__ __forceinline__ void load4(const void* base, int64_t off, float (&o)[4]) {
+    const uint2* p = reinterpret_cast<const uint2*>(static_cast<const uint16_t*>(base) + off);
+    uint2 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p));
+    o[0] = __uint_as_float(v.x << 16);
+    o[1] = __uint_as_float(v.x & 0xffff0000u);
+    o[2] = __uint_as_float(v.y << 16);
+    o[3] = __uint_as_float(v.y & 0xffff0000u);
+  }
+  static __device__ __forceinline__ float load1(const void* base, int64_t off) {
+    return __uint_as_float(static_cast<uint32_t>(__ldg(static_cast<const uint16_t*>(base) + off)) << 16);
+  }
+};
+template <>
+struct Elem<LANTERN_F16> {
+  static constexpr int kBytes = 2;
+  static __device__ __forceinline__ void load4(const void* base, int64_t off, float (&o)[4]) {
+    const uint2* p = reinterpret_cast<const uint2*>(static_cast<const uint16_t*>(base) + off);
+    uint2 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p));
+    float2 a = __half22float2(*reinterpret_cast<__half2*>(&v.x));
+    float2 b = __half22float2(*reinterpret_cast<__half2*>(&v.y));
+    o[0] = a.x; o[1] = a.y; o[2] = b.x; o[3] = b.y;
+  }
+  static __device__ __forceinline__ float load1(const void* base, int64_t off) {
+    __half h = __ushort_as_half(__ldg(static_cast<const uint16_t*>(base) + off));
+    return __half2float(h);
+  }
+};
+
+// CFG mix + temperature, one separately rounded fp32 op per reference ATen kernel
+// (ea_model_llamagen.py:28: uncond + (cond - uncond) * scale; HF TemperatureLogitsWarper: scores / T).
+// The intrinsics forbid FMA contraction so the value is bit-identical to the reference arithmetic.
+struct MixParams {
+  float cfg_scale;
+  float temperature;
+  int has_uncond;
+  int do_temp;
+};
+__device__ __forceinline__ float mix_temper(float c, float u, const MixParams& m) {
+  float v = c;
+  if (m.has_uncond) v = __fadd_rn(u, __fmul_rn(__fsub_rn(c, u), m.cfg_scale));
+  if (m.do_temp) v = __fdiv_rn(v, m.temperature);
+  return v;
+}
+
+// Monotone float -> uint32 key (larger float => larger key; -0 < +0 only as keys).
+__device__ __forceinline__ uint32_t float_key(float f) {
+  uint32_t b = __float_as_uint(f);
+  return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__device__ __forceinline__ float key_float(uint32_t k) {
+  uint32_t b = (k & 0x80000000u) ? (k & 0x7fffffffu) : ~k;
+  return __uint_as_float(b);
+}
+
+// ----------------------------------------------------------------------------------------------
+// Warp / block reductions.  `scratch` must hold >= 33 elements of T and is reusable after return.
+// ----------------------------------------------------------------------------------------------
+template <typename T, typename Op>
+__device__ __forceinline__ T warp_reduce(T v, Op op) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = op(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+template <typename T, typename Op>
+__device__ __forceinline__ T block_reduce(T v, Op op, T identity, T* scratch) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = (blockDim.x + 31) >> 5;
+  v = warp_reduce(v, op);
+  __syncthreads();  // protect scratch from a previous use
+  if (lane == 0) scratch[warp] = v;
+  __syncthreads();
+  if (warp == 0) {
+    T w = lane < nwarp ? scratch[lane] : identity;
+    w = warp_reduce(w, op);
+    if (lane == 0) scratch[32] = w;
+  }
+  __syncthreads();
+  return scratch[32];
+}
+
+struct OpSum {
+  template <typename T>
+  __device__ __forceinline__ T operator()(T a, T b) const { return a + b; }
+};
+struct OpMaxF {
+  __device__ __forceinline__ float operator()(float a, float b) const { return fmaxf(a, b); }
+};
+struct OpMinI {
+  __device__ __forceinline__ int operator()(int a, int b) const { return a < b ? a : b; }
+};
+struct OpMaxI {
+  __device__ __forceinline__ int operator()(int a, int b) const { return a > b ? a : b; }
+};
+
+// Block-wide scan of doubles: returns this thread's inclusive prefix, *total gets the block sum.
+__device__ __forceinline__ double block_scan_incl(double v, double* scratch, double* total) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = (blockDim.x + 31) >> 5;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    double n = __shfl_up_sync(0xffffffffu, v, o);
+    if (lane >= o) v += n;
+  }
+  __syncthreads();
+  if (lane == 31) scratch[warp] = v;
+  __syncthreads();
+  double pre = 0.0, tot = 0.0;
+  for (int w = 0; w < nwarp; ++w) {
+    double t = scratch[w];
+    if (w < warp) pre += t;
+    tot += t;
+  }
+  *total = tot;
+  return pre + v;
+}
+
+// ----------------------------------------------------------------------------------------------
+// Philox-4x32-10 (Salmon et al. 2011).  Stream contract (shared with oracle/lantern_oracle.py
+// philox_uniforms and lantern_philox_uniforms): draw d of item b at verify step s is word d%4 of
+// philox(counter = (d/4, s_lo, b, s_hi), key = seed), mapped to [0,1) as (w >> 8) * 2^-24.
+// ----------------------------------------------------------------------------------------------
+__host__ __device__ __forceinline__ void philox4x32_10(uint32_t (&c)[4], uint32_t k0, uint32_t k1) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    uint64_t p0 = 0xD2511F53ull * c[0];
+    uint64_t p1 = 0xCD9E8D57ull * c[2];
+    uint32_t n0 = static_cast<uint32_t>(p1 >> 32) ^ c[1] ^ k0;
+    uint32_t n1 = static_cast<uint32_t>(p1);
+    uint32_t n2 = static_cast<uint32_t>(p0 >> 32) ^ c[3] ^ k1;
+    uint32_t n3 = static_cast<uint32_t>(p0);
+    c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3;
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+}
+__host__ __device__ __forceinline__ float philox_uniform(uint64_t seed, uint64_t step, uint32_t item,
+                                                         uint32_t draw) {
+  uint32_t c[4] = {draw >> 2, static_cast<uint32_t>(step), item, static_cast<uint32_t>(step >> 32)};
+  philox4x32_10(c, static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32));
+  return static_cast<float>(c[draw & 3] >> 8) * (1.0f / 16777216.0f);
+}
+
+}  // namespace lantern

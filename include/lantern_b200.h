@@ -152,6 +152,12 @@ LANTERN_API int lantern_accept_fused(const lantern_accept_cfg* cfg, const lanter
                          const lantern_accept_out* out, void* workspace_dev, size_t workspace_bytes,
                          void* stream);
 
+/* Measurement hook: the same step restricted to some phases (bit 0: per-row statistics kernel, bit 1: walk
+ * kernel).  bench.py uses it to time the HBM-bound kernel on its own; phases == 3 is lantern_accept_fused. */
+LANTERN_API int lantern_accept_phases(const lantern_accept_cfg* cfg, const lantern_accept_in* in,
+                                      const lantern_accept_out* out, void* workspace_dev, size_t workspace_bytes,
+                                      void* stream, int phases);
+
 /*
  * Bonus-token draw from caller-supplied probability rows (update_inference_inputs given a
  * sample_p that did not come from lantern_accept_fused): token[b] = min{i : cdf_i > u[b] * total}.

@@ -19,6 +19,7 @@ OK, E_INVALID, E_UNSUPPORTED, E_WORKSPACE, E_NO_DEVICE = 0, -1, -2, -3, -4
 
 EXPORTS = (
     "lantern_version", "lantern_last_error", "lantern_accept_workspace_bytes", "lantern_accept_fused",
+    "lantern_accept_phases",
     "lantern_sample_tokens", "lantern_kv_compact", "lantern_build_neighbors", "lantern_philox_uniforms",
     "lantern_session_create", "lantern_session_step", "lantern_session_destroy",
 )
@@ -92,6 +93,8 @@ def load() -> C.CDLL:
     lib.lantern_accept_fused.restype = C.c_int
     lib.lantern_accept_fused.argtypes = [C.POINTER(AcceptCfg), C.POINTER(AcceptIn), C.POINTER(AcceptOut),
                                          C.c_void_p, C.c_size_t, C.c_void_p]
+    lib.lantern_accept_phases.restype = C.c_int
+    lib.lantern_accept_phases.argtypes = lib.lantern_accept_fused.argtypes + [C.c_int]
     lib.lantern_sample_tokens.restype = C.c_int
     lib.lantern_sample_tokens.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
                                           C.c_void_p]

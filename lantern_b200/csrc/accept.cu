@@ -586,14 +586,15 @@ static size_t walk_smem_bytes(const lantern_accept_cfg& c) {
 }
 
 template <int DT, bool VEC>
-static int launch_all(const AcceptParams& P, cudaStream_t stream) {
+static int launch_all(const AcceptParams& P, cudaStream_t stream, int phases) {
   const lantern_accept_cfg& c = P.cfg;
   const long long rows = (long long)c.n_items * c.n_rows;
   const int nquads = (c.ncols + 3) / 4;
   const int nq = (nquads + kStatThreads - 1) / kStatThreads;
   const int grid = (int)std::min<long long>(rows, (long long)kNumSMs * 4);
 #define LAUNCH_STATS(NQ) row_stats_kernel<DT, NQ, VEC><<<grid, kStatThreads, 0, stream>>>(P)
-  if (nq <= 1) LAUNCH_STATS(1);
+  if (!(phases & 1)) {
+  } else if (nq <= 1) LAUNCH_STATS(1);
   else if (nq <= 2) LAUNCH_STATS(2);
   else if (nq <= 4) LAUNCH_STATS(4);
   else if (nq <= 8) LAUNCH_STATS(8);
@@ -604,6 +605,7 @@ static int launch_all(const AcceptParams& P, cudaStream_t stream) {
   }
 #undef LAUNCH_STATS
   LANTERN_CUDA(cudaGetLastError());
+  if (!(phases & 2)) return LANTERN_OK;
   const size_t smem = walk_smem_bytes(c);
   if (smem > 227 * 1024) {
     set_error("walk kernel needs %zu bytes of shared memory (> 227 KB): ncols too large", smem);
@@ -658,6 +660,12 @@ static int validate(const lantern_accept_cfg& c, const lantern_accept_in& in, co
 extern "C" int lantern_accept_fused(const lantern_accept_cfg* cfg, const lantern_accept_in* in,
                                     const lantern_accept_out* out, void* workspace_dev, size_t workspace_bytes,
                                     void* stream) {
+  return lantern_accept_phases(cfg, in, out, workspace_dev, workspace_bytes, stream, 3);
+}
+
+extern "C" int lantern_accept_phases(const lantern_accept_cfg* cfg, const lantern_accept_in* in,
+                                     const lantern_accept_out* out, void* workspace_dev, size_t workspace_bytes,
+                                     void* stream, int phases) {
   if (!cfg || !in || !out) {
     set_error("lantern_accept_fused: null argument");
     return LANTERN_E_INVALID;
@@ -694,7 +702,7 @@ extern "C" int lantern_accept_fused(const lantern_accept_cfg* cfg, const lantern
              (cfg->item_stride % 4 == 0) && aligned(in->logits_cond) && aligned(in->logits_uncond);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
 #define DISPATCH(DT)                                        \
-  return P.vec_ok ? launch_all<DT, true>(P, s) : launch_all<DT, false>(P, s)
+  return P.vec_ok ? launch_all<DT, true>(P, s, phases) : launch_all<DT, false>(P, s, phases)
   switch (cfg->logits_dtype) {
     case LANTERN_F32: DISPATCH(LANTERN_F32);
     case LANTERN_BF16: DISPATCH(LANTERN_BF16);

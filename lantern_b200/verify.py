@@ -141,7 +141,8 @@ class Verifier:
              retrieve: Optional[torch.Tensor] = None, *, row_kinds: Optional[torch.Tensor] = None,
              uniforms: Optional[torch.Tensor] = None, philox: Tuple[int, int] = (0, 0),
              node_q: Optional[torch.Tensor] = None, draft_op: Optional[torch.Tensor] = None,
-             sib_tokens: Optional[torch.Tensor] = None, want_sample_p: bool = False) -> VerifyResult:
+             sib_tokens: Optional[torch.Tensor] = None, want_sample_p: bool = False,
+             phases: int = 3) -> VerifyResult:
         """logits_*: [B, T, V] (fp32/bf16/fp16, last dim contiguous); tree_tokens: [B, T] int32;
         retrieve: [B, L, D] or [L, D] int32 (defaults to the static tree's).  Asynchronous."""
         if logits_cond.dim() != 3 or logits_cond.stride(2) != 1:
@@ -201,8 +202,8 @@ class Verifier:
         if self._work is None or self._work.numel() < need or self._work.device != dev:
             self._work = torch.empty(max(need, 1), dtype=torch.uint8, device=dev)
         stream = torch.cuda.current_stream(dev).cuda_stream
-        _abi.check(self.lib.lantern_accept_fused(C.byref(cfg), C.byref(ain), C.byref(aout), self._work.data_ptr(),
-                                                 self._work.numel(), stream))
+        _abi.check(self.lib.lantern_accept_phases(C.byref(cfg), C.byref(ain), C.byref(aout), self._work.data_ptr(),
+                                                  self._work.numel(), stream, phases))
         res._keepalive = (logits_cond, logits_uncond, tree_tokens, retrieve, row_kinds, uniforms, node_q, draft_op)
         return res
 

@@ -46,7 +46,7 @@ class Built:
 def default_params(**kw) -> dict:
     p = dict(family="llamagen", ncols=None, tree="eagle2", total_tokens=59, depth=4, seed=0,
              lantern=True, lantern_k=1000, lantern_delta=0.1, temperature=1.0, top_k=2000, top_p=1.0,
-             cfg_scale=3.0, cfg=True, boost=13.0, static_tree=None, newline_depth=-1, sharp=1.0)
+             cfg_scale=3.0, cfg=True, boost=13.0, static_tree=None, newline_depth=-1, sharp=1.0, table_seed=0)
     p.update(kw)
     return p
 
@@ -113,7 +113,7 @@ def build(params: dict) -> Built:
     table = None
     if p["lantern"]:
         k = min(int(p["lantern_k"]), fam.ncols - 1)
-        table = synth.neighbor_table(seed, fam.ncols, min(k + 1, fam.ncols - 1))
+        table = synth.neighbor_table(p["table_seed"], fam.ncols, min(k + 1, fam.ncols - 1))
     warp = O.Warp(p["temperature"], p["top_p"], p["top_k"])
     u = synth.uniforms(seed, T + 1, stream=77)
     return Built(p, fam, warp, cond, uncond, tree, cand, table, u, row_kinds, static, ssyn, tbuf)

@@ -93,9 +93,18 @@ def compare(res, i: int, orc, tol: float = 1e-5, check_token: bool = True):
     if check_token:
         assert int(res.token[i]) == orc.token, f"token {int(res.token[i])} != {orc.token}"
     if res.sample_p is not None:
-        got = res.sample_p[i].cpu().numpy()
-        want = orc.sample_p
-        nz = want > 0
-        assert np.array_equal(got > 0, nz), "support of sample_p differs"
-        err = np.max(np.abs(got[nz] - want[nz]) / want[nz])
-        assert err <= tol, f"sample_p rel err {err}"
+        assert_probs_close(res.sample_p[i].cpu().numpy(), orc.sample_p, tol)
+
+
+def assert_probs_close(got: np.ndarray, want: np.ndarray, rtol: float = 1e-5):
+    """north_star tolerance: 1e-5 relative in fp32.  Static-tree residuals are differences
+    ``max(p - q, 0)`` of nearly equal numbers, so an absolute floor of 1e-6 x the largest entry is allowed
+    (cancellation amplifies the ~1e-7 relative difference between two correct softmax implementations)."""
+    atol = 1e-6 * float(want.max())
+    err = np.abs(got.astype(np.float64) - want.astype(np.float64))
+    bad = err > rtol * np.abs(want) + atol
+    assert not bad.any(), (f"{int(bad.sum())} probabilities differ; worst abs err {err.max():.3e} "
+                           f"at {int(err.argmax())}: got {got[err.argmax()]!r} want {want[err.argmax()]!r}")
+    big = want > 10 * atol
+    assert np.all(got[big] > 0), "support of sample_p differs"
+    assert np.all(got[want == 0] <= atol)

@@ -1,0 +1,433 @@
+#!/usr/bin/env python
+"""Benchmark of the LANTERN verification hot path (see DESIGN.md "Measurement").
+
+    python bench.py --gpus N --steps K --warmup W            # B200 arm (prints ONE JSON line on rank 0)
+    python bench.py --impl reference --gpus N --steps K ...  # CPU arm: the reference algorithm on host cores
+
+A "step" is one verify step (tree_decoding post-processing -> evaluate_posterior -> bonus token) over one batch
+of ``--items`` prompts of synthetic logits of the named family's shapes.  Default workload = BASELINE.json
+configs[1]: Lumina-mGPT 768px shapes (V=65536, 8192 image tokens, CFG-doubled logits, top-k 2000, cfg 3.0),
+EAGLE-2 tree of 59 nodes / depth 5, LANTERN k=1000 delta=0.1.  The 7B target / drafter forward passes are not
+part of this path and are not run.
+
+value  = images/s of the verification path with inputs resident in HBM:
+         tokens emitted per second (sum over prompts of accept_length+1) / tokens per image.
+e2e    = the same through the host-buffer session call (lantern_session_step): logits in pinned host memory,
+         host->device copy of the live logits window and device->host copy of the results inside the timed region.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for _p in (ROOT, os.path.join(ROOT, "tests")):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+TOKENS_PER_IMAGE = {"lumina_mgpt": 2354, "anole": 1024, "llamagen": 256}   # generate_images.py:209,215-218
+DEPTH = {"lumina_mgpt": 5, "anole": 4, "llamagen": 4}                       # ea_model_*.from_pretrained defaults
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--family", default="lumina_mgpt", choices=list(TOKENS_PER_IMAGE))
+    ap.add_argument("--items", type=int, default=64, help="prompts per GPU per step")
+    ap.add_argument("--total-tokens", type=int, default=59)
+    ap.add_argument("--logits-dtype", default="fp32", choices=["fp32", "bf16"])
+    ap.add_argument("--lantern-k", type=int, default=1000)
+    ap.add_argument("--lantern-delta", type=float, default=0.1)
+    ap.add_argument("--top-k", type=int, default=2000)
+    ap.add_argument("--cfg", type=float, default=3.0)
+    ap.add_argument("--pool", type=int, default=3, help="distinct input batches cycled through (each > L2)")
+    ap.add_argument("--cpu-items", type=int, default=0, help="items in the CPU sample (0 = auto)")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------
+# Synthetic workload
+# ------------------------------------------------------------------------------------------------
+def host_trees(family, total_tokens, n, seed0):
+    """n EAGLE-2-shaped trees with sibling-distinct image tokens (host, deterministic)."""
+    from lantern_b200 import synth
+    from lantern_b200.verify import FAMILIES
+    fam = FAMILIES[family]
+    out = []
+    for i in range(n):
+        t = synth.eagle2_tree(seed0 + i, total_tokens, DEPTH[family])
+        synth.assign_tokens(seed0 + i, t, fam.col0, fam.col0 + fam.ncols)
+        out.append(t)
+    return out
+
+
+def pad_ri(trees):
+    L = max(t.retrieve_indices.shape[0] for t in trees)
+    D = max(t.retrieve_indices.shape[1] for t in trees)
+    ri = np.full((len(trees), L, D), -1, dtype=np.int32)
+    for i, t in enumerate(trees):
+        r = t.retrieve_indices
+        ri[i, :r.shape[0], :r.shape[1]] = r
+    return ri
+
+
+def device_batch(args, fam, trees, seed, device):
+    """One batch of device-resident inputs: cond/uncond [B,T,V], tokens [B,T], retrieve [B,L,D], uniforms."""
+    import torch
+    B, T, V = len(trees), trees[0].T, fam.vocab
+    g = torch.Generator(device=device)
+    g.manual_seed(seed)
+    dt = torch.float32 if args.logits_dtype == "fp32" else torch.bfloat16
+    cond = torch.empty(B, T, V, device=device, dtype=torch.float32)
+    cond.normal_(0.0, 2.31, generator=g)
+    uncond = torch.empty(B, T, V, device=device, dtype=torch.float32)
+    uncond.normal_(0.0, 0.8, generator=g)
+    uncond += cond
+    tok = np.stack([t.tokens for t in trees]).astype(np.int64)
+    par = np.stack([t.parent for t in trees]).astype(np.int64)
+    bi = np.repeat(np.arange(B)[:, None], T - 1, axis=1).reshape(-1)
+    pi, ti = par[:, 1:].reshape(-1), tok[:, 1:].reshape(-1)
+    idx = (torch.from_numpy(bi).to(device), torch.from_numpy(pi).to(device), torch.from_numpy(ti).to(device))
+    boost = torch.full((bi.shape[0],), 13.0, device=device)
+    cond.index_put_(idx, boost, accumulate=True)
+    uncond.index_put_(idx, boost, accumulate=True)
+    cond, uncond = cond.to(dt), uncond.to(dt)
+    tokens = torch.from_numpy(tok.astype(np.int32)).to(device)
+    retrieve = torch.from_numpy(pad_ri(trees)).to(device)
+    uni = torch.rand(B, T + 1, device=device, generator=g)
+    return dict(cond=cond, uncond=uncond, tokens=tokens, retrieve=retrieve, uniforms=uni)
+
+
+# ------------------------------------------------------------------------------------------------
+# Clocks
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self._stop, self._t = index, [], threading.Event(), None
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                      "-i", str(self.index)], capture_output=True, text=True, timeout=5).stdout
+                parts = [x.strip() for x in out.strip().split(",")]
+                if len(parts) >= 6:
+                    self.rows.append(parts)
+            except Exception:
+                pass
+            self._stop.wait(0.1)
+
+    def __enter__(self):
+        self._t = threading.Thread(target=self._run, daemon=True)
+        self._t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self._t.join(timeout=6)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        sm = sorted(float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(r[2 + i].lower().startswith("active") for r in self.rows)]
+        mx = [float(r[1]) for r in self.rows if r[1].replace(".", "").isdigit()]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(self.rows)}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: the reference algorithm (oracle port, eager like the reference) on the host cores
+# ------------------------------------------------------------------------------------------------
+def _cpu_item(job):
+    """One prompt, one verify step, reference cost structure (all T rows post-processed + [L,D,V] gather)."""
+    family, total_tokens, seed, k, delta, top_k, cfg, reps = job
+    import casegen as C
+    b = C.build(dict(family=family, seed=seed, total_tokens=total_tokens, depth=DEPTH[family], lantern_k=k,
+                     lantern_delta=delta, top_k=top_k, cfg_scale=cfg))
+    from oracle import lantern_oracle as O
+    kk = min(k, b.fam.ncols - 1)
+    t0 = time.perf_counter()
+    tokens = 0
+    for _ in range(reps):
+        r = O.verify_step(b.cond, b.uncond, cfg, b.tree.tokens, b.tree.retrieve_indices, b.uniforms, b.fam, b.warp,
+                          True, kk, delta, b.table, row_kinds=b.row_kinds, eager=True)
+        tokens += r.accept_length + 1
+    return time.perf_counter() - t0, tokens
+
+
+def cpu_reference(args, n_items, reps, cores):
+    """Returns (images/s, seconds of wall time, tokens) for n_items x reps verify steps on `cores` processes."""
+    import multiprocessing as mp
+    jobs = [(args.family, args.total_tokens, 90000 + i, args.lantern_k, args.lantern_delta, args.top_k, args.cfg, reps)
+            for i in range(n_items)]
+    ctx = mp.get_context("fork")
+    with ctx.Pool(cores) as pool:
+        pool.map(_cpu_item, jobs[:cores])                 # build caches / warm numpy
+        t0 = time.perf_counter()
+        res = pool.map(_cpu_item, jobs, chunksize=1)
+        wall = time.perf_counter() - t0
+    # the timed region should be the verify steps, not input synthesis: use the summed in-step time / cores
+    step_time = sum(r[0] for r in res) / cores
+    tokens = sum(r[1] for r in res)
+    return tokens / step_time / TOKENS_PER_IMAGE[args.family], step_time, tokens, wall
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    n_items = args.cpu_items or max(cores, 16)
+    vals = []
+    for _ in range(args.warmup > 0 and 1 or 0):
+        cpu_reference(args, min(n_items, cores), 1, cores)
+    t_all, tok_all = 0.0, 0
+    for _ in range(args.steps):
+        v, st, tok, _ = cpu_reference(args, n_items, 1, cores)
+        t_all += st
+        tok_all += tok
+    value = tok_all / t_all / TOKENS_PER_IMAGE[args.family]
+    line = {
+        "impl": "reference", "metric": "images/sec (verification hot path)", "value": value, "unit": "images/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_all / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, n_items),
+        "cpu_baseline": {"value": value, "unit": "images/s", "cores": cores, "kind": "port",
+                         "sample": f"{n_items} prompts x {args.steps} verify steps, oracle/lantern_oracle.py eager "
+                                   f"(all T rows post-processed + [L,D,V] gather, as the reference does), one process per core"},
+        "e2e": {"value": value, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def workload_config(args, items):
+    from lantern_b200.verify import FAMILIES
+    fam = FAMILIES[args.family]
+    return {"workload": f"{args.family} verify step (BASELINE configs[1] shapes)" if args.family == "lumina_mgpt"
+            else f"{args.family} verify step", "family": args.family, "vocab": fam.vocab, "image_tokens": fam.ncols,
+            "prompts_per_gpu": items, "tree": f"EAGLE-2 dynamic, {args.total_tokens} nodes, depth {DEPTH[args.family]}",
+            "cfg_scale": args.cfg, "top_k": args.top_k, "temperature": 1.0, "lantern_k": args.lantern_k,
+            "lantern_delta": args.lantern_delta, "logits": args.logits_dtype,
+            "tokens_per_image": TOKENS_PER_IMAGE[args.family],
+            "l2_policy": "inputs larger than L2: a pool of distinct batches, each > 126 MB of live logits"}
+
+
+# ------------------------------------------------------------------------------------------------
+# B200 arm
+# ------------------------------------------------------------------------------------------------
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    from lantern_b200 import _abi, verify, synth
+    import ctypes as C
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the B200 arm has no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    fam = verify.FAMILIES[args.family]
+    B, T = args.items, args.total_tokens
+    k = min(args.lantern_k, fam.ncols - 1)
+    table_np = synth.neighbor_table(0, fam.ncols, k + 1)
+    table = torch.from_numpy(table_np).to(dev)
+    ver = verify.Verifier(fam, temperature=1.0, top_k=args.top_k, cfg_scale=args.cfg, lantern=True, lantern_k=k,
+                          lantern_delta=args.lantern_delta, nbr_table=table, device=dev)
+    tree_pool = host_trees(args.family, T, 16, 1000 + 97 * rank)
+    batches = []
+    for p in range(args.pool):
+        trees = [tree_pool[(i + 5 * p) % len(tree_pool)] for i in range(B)]
+        batches.append(device_batch(args, fam, trees, 1234 + 1000 * rank + p, dev))
+    eb = 4 if args.logits_dtype == "fp32" else 2
+
+    def step(i, phases=3):
+        bt = batches[i % len(batches)]
+        return ver.step(bt["cond"], bt["uncond"], bt["tokens"], bt["retrieve"], uniforms=bt["uniforms"], phases=phases)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(max(args.warmup, 3)):
+        step(i)
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    results = []
+    with ClockSampler(local) as clocks:
+        ev0.record()
+        for i in range(args.steps):
+            results.append(step(i))
+        ev1.record()
+        torch.cuda.synchronize()
+        ms = ev0.elapsed_time(ev1)
+        # dominant kernel alone (row statistics), same inputs, events on the launching stream
+        for i in range(3):
+            step(i, phases=1)
+        torch.cuda.synchronize()
+        k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        k0.record()
+        for i in range(args.steps):
+            step(i, phases=1)
+        k1.record()
+        torch.cuda.synchronize()
+        ms_stats = k0.elapsed_time(k1) / args.steps
+    tokens = sum(int((r.accept_length.sum() + B).item()) for r in results)
+    accept_mean = tokens / (args.steps * B)
+
+    # ---- end to end through the host-buffer session (pinned host logits) ----
+    e2e = None
+    if not args.no_e2e:
+        e2e = run_e2e(args, fam, ver, table_np, tree_pool, rank, dev, world)
+
+    t = torch.tensor([ms], device=dev, dtype=torch.float64)
+    tk = torch.tensor([float(tokens)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tk, op=dist.ReduceOp.SUM)
+        if e2e is not None:
+            mx = torch.tensor([e2e["ms"]], device=dev, dtype=torch.float64)
+            sm = torch.tensor([float(e2e["tokens"])], device=dev, dtype=torch.float64)
+            dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+            dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+            e2e["ms"], e2e["tokens"] = float(mx[0]), float(sm[0])
+    ms_all, tokens_all = float(t[0]), float(tk[0])
+    tpi = TOKENS_PER_IMAGE[args.family]
+    value = tokens_all / (ms_all * 1e-3) / tpi
+
+    if rank == 0:
+        peaks = {}
+        try:
+            with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+                peaks = json.load(f)
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        stat_bytes = B * 2 * T * fam.ncols * eb           # algorithmic bytes of the row-statistics kernel
+        achieved = stat_bytes / (ms_stats * 1e-3) / 1e9
+        n_try = float(np.mean([float(r.n_draws.float().mean().item()) - 1 for r in results]))
+        step_bytes = B * (2 * T * fam.ncols * eb + n_try * (k + 1) * 4 + 16)
+        traffic = None
+        try:
+            with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+                traffic = json.load(f).get(f"{args.family}_{args.logits_dtype}_B{B}_T{T}")
+        except Exception:
+            pass
+        line = {
+            "metric": "images/sec (verification hot path)", "value": value, "unit": "images/s",
+            "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_all / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(args, B),
+            "mean_accept_length": accept_mean,
+            "verify_steps_per_s": world * B * args.steps / (ms_all * 1e-3),
+            "accept_step_gbs": step_bytes / (ms_all / args.steps * 1e-3) / 1e9,
+            "clocks": clocks.summary(),
+            "gpu_launches": 2 * args.steps,
+            "roofline": {"bound": "hbm", "kernel": "row_stats_kernel", "achieved": achieved, "peak": peak,
+                         "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                         "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst; kernel timed alone)" if peaks else "fallback 6650 GB/s",
+                         "bytes_per_launch": stat_bytes, "ms_per_launch": ms_stats,
+                         "frac_of_nominal_8TBs": achieved / 8000.0},
+        }
+        if e2e is not None:
+            line["e2e"] = {"value": e2e["tokens"] / (e2e["ms"] * 1e-3) / tpi, "unit": "images/s",
+                           "h2d_bytes_per_step": e2e["h2d"], "d2h_bytes_per_step": e2e["d2h"],
+                           "ms_per_step": e2e["ms"] / e2e["steps"], "steps": e2e["steps"]}
+        if not args.no_cpu and world >= 1:
+            cores = os.cpu_count() or 1
+            n_items = args.cpu_items or max(cores, 16)
+            v, st, tok, wall = cpu_reference(args, n_items, 2, cores)
+            line["cpu_baseline"] = {"value": v, "unit": "images/s", "cores": cores, "kind": "port",
+                                    "sample": f"{n_items} prompts x 2 verify steps of the same workload, "
+                                              f"oracle/lantern_oracle.py eager, one process per core ({wall:.1f}s wall)"}
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def run_e2e(args, fam, ver, table_np, tree_pool, rank, dev, world):
+    """Host-buffer path: pinned host logits -> lantern_session_step (H2D window copy + kernels + D2H results)."""
+    import ctypes as C
+    import torch
+    from lantern_b200 import _abi
+    lib = _abi.load()
+    B, T, V = args.items, args.total_tokens, fam.vocab
+    dt = torch.float32 if args.logits_dtype == "fp32" else torch.bfloat16
+    trees = [tree_pool[i % len(tree_pool)] for i in range(B)]
+    hb = device_batch(args, fam, trees, 777 + rank, dev)
+    host = {}
+    for name in ("cond", "uncond"):
+        h = torch.empty(hb[name].shape, dtype=dt, pin_memory=True)
+        h.copy_(hb[name])
+        host[name] = h
+    tokens = hb["tokens"].cpu().pin_memory()
+    retrieve = hb["retrieve"].cpu().pin_memory()
+    uni = hb["uniforms"].cpu().pin_memory()
+    L, D = retrieve.shape[1:]
+    del hb
+    torch.cuda.synchronize()
+    cfg = ver._cfg(B, T, L, D, host["cond"], False, T + 1, (0, 0))
+    sess = C.c_void_p()
+    _abi.check(lib.lantern_session_create(C.byref(cfg), table_np.ctypes.data, table_np.shape[0], C.byref(sess)))
+    ain = _abi.AcceptIn()
+    ain.logits_cond, ain.logits_uncond = host["cond"].data_ptr(), host["uncond"].data_ptr()
+    ain.tree_tokens, ain.retrieve, ain.uniforms = tokens.data_ptr(), retrieve.data_ptr(), uni.data_ptr()
+    out_np = {n: np.zeros(B, dtype=np.int32) for n in ("accept_length", "best_candidate", "token", "n_draws", "flags")}
+    path = np.zeros((B, D), dtype=np.int32)
+    sel = np.zeros((B, D), dtype=np.int32)
+    aout = _abi.AcceptOut()
+    aout.accept_length, aout.best_candidate = out_np["accept_length"].ctypes.data, out_np["best_candidate"].ctypes.data
+    aout.token, aout.n_draws, aout.flags = out_np["token"].ctypes.data, out_np["n_draws"].ctypes.data, out_np["flags"].ctypes.data
+    aout.path_tokens, aout.select_indices = path.ctypes.data, sel.ctypes.data
+    steps = max(3, min(args.steps, 10))
+    for _ in range(2):
+        _abi.check(lib.lantern_session_step(sess, C.byref(cfg), C.byref(ain), C.byref(aout)))
+    torch.cuda.synchronize()
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+    t0 = time.perf_counter()
+    tok = 0
+    for _ in range(steps):
+        _abi.check(lib.lantern_session_step(sess, C.byref(cfg), C.byref(ain), C.byref(aout)))   # synchronous
+        tok += int(out_np["accept_length"].sum()) + B
+    ms = (time.perf_counter() - t0) * 1e3
+    lib.lantern_session_destroy(sess)
+    eb = 4 if args.logits_dtype == "fp32" else 2
+    width = ((fam.col0 + fam.ncols + 7) & ~7) - (fam.col0 & ~7)
+    h2d = 2 * B * T * width * eb + tokens.numel() * 4 + retrieve.numel() * 4 + uni.numel() * 4
+    d2h = B * (5 + 2 * D) * 4
+    return {"ms": ms, "tokens": tok, "steps": steps, "h2d": h2d, "d2h": d2h}
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_b200(a)

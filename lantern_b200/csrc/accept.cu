@@ -15,9 +15,11 @@
 //
 // Reference semantics: SURVEY.md Appendix A; file:line citations are in include/lantern_b200.h.
 #include <algorithm>
+#include <cmath>
 #include <cstdio>
 
 #include "common.cuh"
+#include "select.cuh"
 
 namespace lantern {
 
@@ -44,9 +46,10 @@ struct AcceptParams {
   int tail_raw;   // vanilla: tail row softmax without the processors
   int lumina;
   int static_zero_q;  // static + relaxed rejection zeroes neighbours in q (LlamaGen/Anole) instead of gtp
+  float z_guess;      // inverse normal CDF of 1 - top_k/ncols: first bracket of the top-k select
+  float win_sd;       // half-width of that bracket in standard deviations
 };
 
-constexpr int kStatThreads = 512;
 constexpr int kWalkThreads = 512;
 constexpr int kMaxSib = 64;
 
@@ -55,65 +58,17 @@ __device__ __forceinline__ bool kept_col(float s, int idx, const RowStats& st) {
 }
 
 // ----------------------------------------------------------------------------------------------
-// Exact k-th largest of the block's register-resident keys: MSB-first radix select, 8 bits per pass,
-// shared-memory histograms.  Returns the key K with count(key > K) < k <= count(key >= K).
-// ----------------------------------------------------------------------------------------------
-template <int NE>
-__device__ __forceinline__ uint32_t radix_select_kth(const float (&s)[NE], int k, unsigned* hist /*[258]*/) {
-  uint32_t prefix = 0, mask = 0;
-  int krem = k;
-  const int tid = threadIdx.x;
-#pragma unroll 1
-  for (int shift = 24; shift >= 0; shift -= 8) {
-    for (int i = tid; i < 256; i += blockDim.x) hist[i] = 0;
-    __syncthreads();
-#pragma unroll
-    for (int e = 0; e < NE; ++e) {
-      const uint32_t key = float_key(s[e]);
-      if ((key & mask) == prefix) atomicAdd(&hist[(key >> shift) & 0xffu], 1u);
-    }
-    __syncthreads();
-    if (tid < 32) {
-      // lane l owns bins [8l, 8l+8); count everything in higher lanes, then walk own bins downwards
-      unsigned c[8], tot = 0;
-#pragma unroll
-      for (int j = 0; j < 8; ++j) { c[j] = hist[tid * 8 + j]; tot += c[j]; }
-      unsigned above = 0;
-      for (int l = 31; l > 0; --l) {
-        const unsigned t = __shfl_sync(0xffffffffu, tot, l);
-        if (tid < l) above += t;
-      }
-      unsigned run = above;
-#pragma unroll
-      for (int j = 7; j >= 0; --j) {
-        if (run < (unsigned)krem && run + c[j] >= (unsigned)krem) {
-          hist[256] = tid * 8 + j;   // selected digit
-          hist[257] = run;           // keys strictly above it (within the current prefix)
-        }
-        run += c[j];
-      }
-    }
-    __syncthreads();
-    prefix |= hist[256] << shift;
-    mask |= 0xffu << shift;
-    krem -= (int)hist[257];
-    __syncthreads();
-  }
-  return prefix;
-}
-
-// ----------------------------------------------------------------------------------------------
 // Phase 1: per-row statistics
 // ----------------------------------------------------------------------------------------------
-template <int DT, int NQ, bool VEC>
-__global__ void __launch_bounds__(kStatThreads) row_stats_kernel(const AcceptParams P) {
+template <int DT, int NT, int NQ, bool VEC>
+__global__ void __launch_bounds__(NT, (NQ * 4 * NT <= 8192 ? 1024 / NT : 512 / NT)) row_stats_kernel(const AcceptParams P) {
   constexpr int NE = NQ * 4;
-  __shared__ unsigned hist[258];
-  __shared__ float fscratch[33];
+  constexpr int NW = NT / 32;
+  __shared__ SelectSmem sm;
   __shared__ double dscratch[33];
 
   const lantern_accept_cfg& cfg = P.cfg;
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const long long n_rows_total = (long long)cfg.n_items * cfg.n_rows;
 
   for (long long row = blockIdx.x; row < n_rows_total; row += gridDim.x) {
@@ -128,47 +83,79 @@ __global__ void __launch_bounds__(kStatThreads) row_stats_kernel(const AcceptPar
     }
     const int64_t base = (int64_t)b * cfg.item_stride + (int64_t)t * cfg.row_stride + cfg.col0;
     float s[NE];
-    // ---- stream the row: all loads are issued before any use ----
-    {
-      float c4[NQ][4], u4[NQ][4];
+    // ---- stream the row (fully unrolled: the loads are hoisted ahead of the arithmetic) ----
 #pragma unroll
-      for (int q = 0; q < NQ; ++q) {
-        const int e0 = (q * kStatThreads + tid) * 4;
-        if (VEC) {
-          if (e0 < cfg.ncols) {
-            Elem<DT>::load4(P.in.logits_cond, base + e0, c4[q]);
-            if (P.mix.has_uncond) Elem<DT>::load4(P.in.logits_uncond, base + e0, u4[q]);
-          }
-        } else {
+    for (int q = 0; q < NQ; ++q) {
+      const int e0 = (q * NT + tid) * 4;
+      float c4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY}, u4[4] = {0.f, 0.f, 0.f, 0.f};
+      if (VEC) {
+        if (e0 < cfg.ncols) {
+          Elem<DT>::load4(P.in.logits_cond, base + e0, c4);
+          if (P.mix.has_uncond) Elem<DT>::load4(P.in.logits_uncond, base + e0, u4);
+        }
+      } else {
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            if (e0 + j < cfg.ncols) {
-              c4[q][j] = Elem<DT>::load1(P.in.logits_cond, base + e0 + j);
-              if (P.mix.has_uncond) u4[q][j] = Elem<DT>::load1(P.in.logits_uncond, base + e0 + j);
-            }
+        for (int j = 0; j < 4; ++j) {
+          if (e0 + j < cfg.ncols) {
+            c4[j] = Elem<DT>::load1(P.in.logits_cond, base + e0 + j);
+            if (P.mix.has_uncond) u4[j] = Elem<DT>::load1(P.in.logits_uncond, base + e0 + j);
           }
         }
       }
 #pragma unroll
-      for (int q = 0; q < NQ; ++q) {
-        const int e0 = (q * kStatThreads + tid) * 4;
+      for (int j = 0; j < 4; ++j) s[q * 4 + j] = mix_temper(c4[j], u4[j], P.mix);   // padding: -inf stays -inf
+    }
+    // ---- row statistics: finite count, sum, sum of squares, min, max (one fused two-level reduction) ----
+    float fsum = 0.f, fsq = 0.f, fmin_ = INFINITY, fmax_ = -INFINITY;
+    int nfin = 0;
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
-          s[q * 4 + j] = (e0 + j < cfg.ncols) ? mix_temper(c4[q][j], P.mix.has_uncond ? u4[q][j] : 0.f, P.mix)
-                                               : -INFINITY;
+    for (int e = 0; e < NE; ++e) {
+      const float v = s[e];
+      fmax_ = fmaxf(fmax_, v);
+      if (v > -INFINITY) {   // skips padding and masked (-inf) logits
+        fsum += v;
+        fsq = fmaf(v, v, fsq);
+        fmin_ = fminf(fmin_, v);
+        ++nfin;
       }
     }
-    // ---- top-k threshold ----
-    if (P.do_topk) st.thr = key_float(radix_select_kth<NE>(s, cfg.top_k, hist));   // padded slots are -inf
-    // ---- softmax statistics over the kept columns ----
-    float m = -INFINITY;
-#pragma unroll
-    for (int e = 0; e < NE; ++e) m = fmaxf(m, s[e]);
-    m = block_reduce(m, OpMaxF(), -INFINITY, fscratch);
+    fsum = warp_reduce(fsum, OpSum());
+    fsq = warp_reduce(fsq, OpSum());
+    fmin_ = -warp_reduce(-fmin_, OpMaxF());
+    fmax_ = warp_reduce(fmax_, OpMaxF());
+    nfin = __reduce_add_sync(0xffffffffu, nfin);
+    __syncthreads();
+    if (lane == 0) {
+      sm.f4[0][warp] = fsum; sm.f4[1][warp] = fsq; sm.f4[2][warp] = fmin_; sm.f4[3][warp] = fmax_;
+      sm.warp_cnt[warp][0] = (unsigned)nfin;
+    }
+    __syncthreads();
+    if (warp == 0) {
+      float a = lane < NW ? sm.f4[0][lane] : 0.f, q2 = lane < NW ? sm.f4[1][lane] : 0.f;
+      float mn = lane < NW ? sm.f4[2][lane] : INFINITY, mx = lane < NW ? sm.f4[3][lane] : -INFINITY;
+      int n = lane < NW ? (int)sm.warp_cnt[lane][0] : 0;
+      a = warp_reduce(a, OpSum()); q2 = warp_reduce(q2, OpSum());
+      mn = -warp_reduce(-mn, OpMaxF()); mx = warp_reduce(mx, OpMaxF());
+      n = __reduce_add_sync(0xffffffffu, n);
+      if (lane == 0) { sm.f_scr[2] = a; sm.f_scr[3] = q2; sm.f_scr[4] = mn; sm.f_scr[5] = mx; sm.i_scr[4] = n; }
+    }
+    __syncthreads();
+    fsum = sm.f_scr[2]; fsq = sm.f_scr[3]; fmin_ = sm.f_scr[4]; fmax_ = sm.f_scr[5]; nfin = sm.i_scr[4];
+    const float m = fmax_;
+    // ---- top-k threshold (exact k-th largest, ties kept by the >= test below) ----
+    if (P.do_topk && cfg.top_k <= nfin) {
+      const float inv_n = 1.0f / (float)nfin;
+      const float mean = fsum * inv_n;
+      const float var = fmaxf(fsq * inv_n - mean * mean, 0.f);
+      st.thr = select_kth_largest<NE>(s, cfg.top_k, fmin_, fmax_, mean, sqrtf(var), P.z_guess, P.win_sd, sm);
+    }
+    // ---- softmax sum over the kept columns ----
+    const ExpShift ex(m);
     float part = 0.f;
 #pragma unroll
     for (int e = 0; e < NE; ++e) {
-      if (s[e] >= st.thr) part += expf(s[e] - m);   // padded slots are -inf -> exp = 0
+      const float ev = ex(s[e]);           // padded / masked slots: ex2(-inf) = 0
+      part += (s[e] >= st.thr) ? ev : 0.f;
     }
     const double tot = block_reduce((double)part, OpSum(), 0.0, dscratch);
     st.mx = m;
@@ -201,6 +188,7 @@ __device__ __forceinline__ void load_probs(const AcceptParams& P, int b, int nod
   MixParams mix = P.mix;
   if (raw) mix.do_temp = 0;
   const float inv = __fdiv_rn(1.0f, st.sum);
+  const ExpShift ex(st.mx);
   const int nquads = (cfg.ncols + 3) >> 2;
   for (int g = threadIdx.x; g < nquads; g += blockDim.x) {
     const int e0 = g * 4;
@@ -222,7 +210,7 @@ __device__ __forceinline__ void load_probs(const AcceptParams& P, int b, int nod
       if (e0 + j < cfg.ncols) {
         const float s = mix_temper(c4[j], u4[j], mix);
         float v = 0.f;
-        if (raw || kept_col(s, e0 + j, st)) v = __fmul_rn(expf(s - st.mx), inv);
+        if (raw || kept_col(s, e0 + j, st)) v = __fmul_rn(ex(s), inv);
         p[e0 + j] = v;
       }
     }
@@ -244,10 +232,11 @@ __device__ __forceinline__ RowStats raw_row_stats(const AcceptParams& P, int b, 
   }
   m = block_reduce(m, OpMaxF(), -INFINITY, fscr);
   float part = 0.f;
+  const ExpShift ex(m);
   for (int e = threadIdx.x; e < cfg.ncols; e += blockDim.x) {
     const float c = Elem<DT>::load1(P.in.logits_cond, base + e);
     const float u = mix.has_uncond ? Elem<DT>::load1(P.in.logits_uncond, base + e) : 0.f;
-    part += expf(mix_temper(c, u, mix) - m);
+    part += ex(mix_temper(c, u, mix));
   }
   const double tot = block_reduce((double)part, OpSum(), 0.0, dscr);
   RowStats st;
@@ -590,17 +579,21 @@ static int launch_all(const AcceptParams& P, cudaStream_t stream, int phases) {
   const lantern_accept_cfg& c = P.cfg;
   const long long rows = (long long)c.n_items * c.n_rows;
   const int nquads = (c.ncols + 3) / 4;
-  const int nq = (nquads + kStatThreads - 1) / kStatThreads;
-  const int grid = (int)std::min<long long>(rows, (long long)kNumSMs * 4);
-#define LAUNCH_STATS(NQ) row_stats_kernel<DT, NQ, VEC><<<grid, kStatThreads, 0, stream>>>(P)
+  // rows up to 8192 columns: 256 threads x up to 32 elements (4 CTAs/SM); larger rows: 512 threads
+  const int nt = c.ncols <= 8192 ? 256 : 512;
+  const int nq = (nquads + nt - 1) / nt;
+  const int grid = (int)std::min<long long>(rows, (long long)kNumSMs * (nt == 256 ? 8 : 4));
+#define LAUNCH_STATS(NT, NQ) row_stats_kernel<DT, NT, NQ, VEC><<<grid, NT, 0, stream>>>(P)
   if (!(phases & 1)) {
-  } else if (nq <= 1) LAUNCH_STATS(1);
-  else if (nq <= 2) LAUNCH_STATS(2);
-  else if (nq <= 4) LAUNCH_STATS(4);
-  else if (nq <= 8) LAUNCH_STATS(8);
-  else if (nq <= 16) LAUNCH_STATS(16);
+  } else if (nt == 256) {
+    if (nq <= 1) LAUNCH_STATS(256, 1);
+    else if (nq <= 2) LAUNCH_STATS(256, 2);
+    else if (nq <= 4) LAUNCH_STATS(256, 4);
+    else LAUNCH_STATS(256, 8);
+  } else if (nq <= 8) LAUNCH_STATS(512, 8);
+  else if (nq <= 16) LAUNCH_STATS(512, 16);
   else {
-    set_error("ncols=%d exceeds the register-resident row limit (%d)", c.ncols, 16 * 4 * kStatThreads);
+    set_error("ncols=%d exceeds the register-resident row limit (%d)", c.ncols, 16 * 4 * 512);
     return LANTERN_E_UNSUPPORTED;
   }
 #undef LAUNCH_STATS
@@ -626,6 +619,29 @@ using namespace lantern;
 extern "C" size_t lantern_accept_workspace_bytes(const lantern_accept_cfg* cfg) {
   if (!cfg) return 0;
   return (size_t)cfg->n_items * (size_t)cfg->n_rows * sizeof(RowStats);
+}
+
+// Acklam's rational approximation of the inverse normal CDF (|error| < 1.2e-9); only seeds a search bracket.
+static double norm_ppf(double p) {
+  static const double a[] = {-3.969683028665376e+01, 2.209460984245205e+02, -2.759285104469687e+02,
+                             1.383577518672690e+02, -3.066479806614716e+01, 2.506628277459239e+00};
+  static const double b[] = {-5.447609879822406e+01, 1.615858368580409e+02, -1.556989798598866e+02,
+                             6.680131188771972e+01, -1.328068155288572e+01};
+  static const double c[] = {-7.784894002430293e-03, -3.223964580411365e-01, -2.400758277161838e+00,
+                             -2.549732539343734e+00, 4.374664141464968e+00, 2.938163982698783e+00};
+  static const double d[] = {7.784695709041462e-03, 3.224671290700398e-01, 2.445134137142996e+00,
+                             3.754408661907416e+00};
+  if (p <= 0.0) return -8.0;
+  if (p >= 1.0) return 8.0;
+  if (p < 0.02425) {
+    const double q = sqrt(-2 * log(p));
+    return (((((c[0] * q + c[1]) * q + c[2]) * q + c[3]) * q + c[4]) * q + c[5]) /
+           ((((d[0] * q + d[1]) * q + d[2]) * q + d[3]) * q + 1);
+  }
+  if (p > 1 - 0.02425) return -norm_ppf(1 - p);
+  const double q = p - 0.5, r = q * q;
+  return (((((a[0] * r + a[1]) * r + a[2]) * r + a[3]) * r + a[4]) * r + a[5]) * q /
+         (((((b[0] * r + b[1]) * r + b[2]) * r + b[3]) * r + b[4]) * r + 1);
 }
 
 static int validate(const lantern_accept_cfg& c, const lantern_accept_in& in, const lantern_accept_out& out) {
@@ -692,6 +708,8 @@ extern "C" int lantern_accept_phases(const lantern_accept_cfg* cfg, const lanter
   P.mix.do_temp = cfg->temperature != 1.0f;
   P.do_topk = cfg->top_k > 0 && cfg->top_k < cfg->ncols;
   P.do_topp = 0;
+  P.z_guess = P.do_topk ? (float)norm_ppf(1.0 - (double)cfg->top_k / (double)cfg->ncols) : 0.f;
+  P.win_sd = 0.15f;
   P.tail_raw = cfg->family == LANTERN_FAMILY_VANILLA;
   P.lumina = cfg->family == LANTERN_FAMILY_LUMINA;
   P.static_zero_q = cfg->static_tree && cfg->family != LANTERN_FAMILY_LUMINA;

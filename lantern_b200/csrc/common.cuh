@@ -92,6 +92,19 @@ __device__ __forceinline__ float mix_temper(float c, float u, const MixParams& m
   return v;
 }
 
+// exp(s - m) for the softmax: one FFMA + MUFU.EX2.  The same function is used wherever a probability is formed
+// (row statistics, walk, tail), so numerator and denominator always agree; relative error <= ~3e-6 for
+// s - m >= -60 (2 ulp of ex2.approx plus the rounding of the scaled argument), inside the 1e-5 budget.
+struct ExpShift {
+  float neg_m_log2e;
+  __device__ __forceinline__ explicit ExpShift(float m) : neg_m_log2e(-m * 1.4426950408889634f) {}
+  __device__ __forceinline__ float operator()(float s) const {
+    float r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(fmaf(s, 1.4426950408889634f, neg_m_log2e)));
+    return r;
+  }
+};
+
 // Monotone float -> uint32 key (larger float => larger key; -0 < +0 only as keys).
 __device__ __forceinline__ uint32_t float_key(float f) {
   uint32_t b = __float_as_uint(f);

@@ -60,16 +60,24 @@ __device__ __forceinline__ bool kept_col(float s, int idx, const RowStats& st) {
 // ----------------------------------------------------------------------------------------------
 // Phase 1: per-row statistics
 // ----------------------------------------------------------------------------------------------
-template <int DT, int NT, int NQ, bool VEC>
-__global__ void __launch_bounds__(NT, (NQ * 4 * NT <= 8192 ? 1024 / NT : 512 / NT)) row_stats_kernel(const AcceptParams P) {
+// MODE 0: generic (bounds-checked, runtime CFG switch, -inf aware statistics).
+// MODE 1: fast path: vector loads, ncols == 4*NT*NQ exactly, CFG-mixed input (logits_uncond present).
+// MODE 2: fast path without logits_uncond.
+template <int DT, int NT, int NQ, bool VEC, int MODE>
+__global__ void __launch_bounds__(NT, (NQ <= 8 ? 1024 / NT : 512 / NT)) row_stats_kernel(const AcceptParams P) {
   constexpr int NE = NQ * 4;
   constexpr int NW = NT / 32;
+  constexpr bool FAST = MODE != 0;
   __shared__ SelectSmem sm;
   __shared__ double dscratch[33];
+  extern __shared__ __align__(16) float park[];   // [NE][NT] thread-private columns of the tier-1 select
 
   const lantern_accept_cfg& cfg = P.cfg;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const long long n_rows_total = (long long)cfg.n_items * cfg.n_rows;
+  const bool has_uncond = MODE == 1 || (MODE == 0 && P.mix.has_uncond);
+  MixParams mix = P.mix;
+  mix.has_uncond = has_uncond;
 
   for (long long row = blockIdx.x; row < n_rows_total; row += gridDim.x) {
     const int b = (int)(row / cfg.n_rows), t = (int)(row % cfg.n_rows);
@@ -82,37 +90,58 @@ __global__ void __launch_bounds__(NT, (NQ * 4 * NT <= 8192 ? 1024 / NT : 512 / N
       continue;
     }
     const int64_t base = (int64_t)b * cfg.item_stride + (int64_t)t * cfg.row_stride + cfg.col0;
+    // pull the next row of this CTA towards L2 while this one is being processed
+    if (tid == 0 && row + gridDim.x < n_rows_total) {
+      const long long nr = row + gridDim.x;
+      const int64_t nbase = (nr / cfg.n_rows) * cfg.item_stride + (nr % cfg.n_rows) * cfg.row_stride + cfg.col0;
+      const size_t eb = Elem<DT>::kBytes;
+      const uintptr_t a0 = (reinterpret_cast<uintptr_t>(P.in.logits_cond) + nbase * eb + 15) & ~uintptr_t(15);
+      const uintptr_t a1 = (reinterpret_cast<uintptr_t>(P.in.logits_cond) + (nbase + cfg.ncols) * eb) & ~uintptr_t(15);
+      if (a1 > a0) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a0), "r"((unsigned)(a1 - a0)));
+      if (has_uncond) {
+        const uintptr_t b0 = (reinterpret_cast<uintptr_t>(P.in.logits_uncond) + nbase * eb + 15) & ~uintptr_t(15);
+        const uintptr_t b1 = (reinterpret_cast<uintptr_t>(P.in.logits_uncond) + (nbase + cfg.ncols) * eb) & ~uintptr_t(15);
+        if (b1 > b0) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(b0), "r"((unsigned)(b1 - b0)));
+      }
+    }
     float s[NE];
     // ---- stream the row (fully unrolled: the loads are hoisted ahead of the arithmetic) ----
 #pragma unroll
     for (int q = 0; q < NQ; ++q) {
       const int e0 = (q * NT + tid) * 4;
       float c4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY}, u4[4] = {0.f, 0.f, 0.f, 0.f};
-      if (VEC) {
+      if (FAST) {
+        Elem<DT>::load4(P.in.logits_cond, base + e0, c4);
+        if (MODE == 1) Elem<DT>::load4(P.in.logits_uncond, base + e0, u4);
+      } else if (VEC) {
         if (e0 < cfg.ncols) {
           Elem<DT>::load4(P.in.logits_cond, base + e0, c4);
-          if (P.mix.has_uncond) Elem<DT>::load4(P.in.logits_uncond, base + e0, u4);
+          if (has_uncond) Elem<DT>::load4(P.in.logits_uncond, base + e0, u4);
         }
       } else {
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           if (e0 + j < cfg.ncols) {
             c4[j] = Elem<DT>::load1(P.in.logits_cond, base + e0 + j);
-            if (P.mix.has_uncond) u4[j] = Elem<DT>::load1(P.in.logits_uncond, base + e0 + j);
+            if (has_uncond) u4[j] = Elem<DT>::load1(P.in.logits_uncond, base + e0 + j);
           }
         }
       }
 #pragma unroll
-      for (int j = 0; j < 4; ++j) s[q * 4 + j] = mix_temper(c4[j], u4[j], P.mix);   // padding: -inf stays -inf
+      for (int j = 0; j < 4; ++j) s[q * 4 + j] = mix_temper(c4[j], u4[j], mix);   // padding: -inf stays -inf
     }
-    // ---- row statistics: finite count, sum, sum of squares, min, max (one fused two-level reduction) ----
+    // ---- row statistics: sum, sum of squares, min, max (+ finite count), one fused two-level reduction ----
     float fsum = 0.f, fsq = 0.f, fmin_ = INFINITY, fmax_ = -INFINITY;
     int nfin = 0;
 #pragma unroll
     for (int e = 0; e < NE; ++e) {
       const float v = s[e];
       fmax_ = fmaxf(fmax_, v);
-      if (v > -INFINITY) {   // skips padding and masked (-inf) logits
+      if (FAST) {            // no padding: masked (-inf) logits are caught below through a non-finite minimum
+        fsum += v;
+        fsq = fmaf(v, v, fsq);
+        fmin_ = fminf(fmin_, v);
+      } else if (v > -INFINITY) {
         fsum += v;
         fsq = fmaf(v, v, fsq);
         fmin_ = fminf(fmin_, v);
@@ -123,7 +152,7 @@ __global__ void __launch_bounds__(NT, (NQ * 4 * NT <= 8192 ? 1024 / NT : 512 / N
     fsq = warp_reduce(fsq, OpSum());
     fmin_ = -warp_reduce(-fmin_, OpMaxF());
     fmax_ = warp_reduce(fmax_, OpMaxF());
-    nfin = __reduce_add_sync(0xffffffffu, nfin);
+    if (!FAST) nfin = __reduce_add_sync(0xffffffffu, nfin);
     __syncthreads();
     if (lane == 0) {
       sm.f4[0][warp] = fsum; sm.f4[1][warp] = fsq; sm.f4[2][warp] = fmin_; sm.f4[3][warp] = fmax_;
@@ -140,14 +169,29 @@ __global__ void __launch_bounds__(NT, (NQ * 4 * NT <= 8192 ? 1024 / NT : 512 / N
       if (lane == 0) { sm.f_scr[2] = a; sm.f_scr[3] = q2; sm.f_scr[4] = mn; sm.f_scr[5] = mx; sm.i_scr[4] = n; }
     }
     __syncthreads();
-    fsum = sm.f_scr[2]; fsq = sm.f_scr[3]; fmin_ = sm.f_scr[4]; fmax_ = sm.f_scr[5]; nfin = sm.i_scr[4];
+    fsum = sm.f_scr[2]; fsq = sm.f_scr[3]; fmin_ = sm.f_scr[4]; fmax_ = sm.f_scr[5];
+    nfin = FAST ? cfg.ncols : sm.i_scr[4];
     const float m = fmax_;
-    // ---- top-k threshold (exact k-th largest, ties kept by the >= test below) ----
-    if (P.do_topk && cfg.top_k <= nfin) {
-      const float inv_n = 1.0f / (float)nfin;
-      const float mean = fsum * inv_n;
-      const float var = fmaxf(fsq * inv_n - mean * mean, 0.f);
-      st.thr = select_kth_largest<NE>(s, cfg.top_k, fmin_, fmax_, mean, sqrtf(var), P.z_guess, P.win_sd, sm);
+    // ---- top-k threshold (exact k-th largest; ties are kept by the >= test below) ----
+    if (P.do_topk) {
+      bool found = false;
+      float thr = -INFINITY;
+      const bool finite = isfinite(fmin_) && isfinite(fmax_) && isfinite(fsq);
+      if (finite && fmin_ == fmax_) { thr = fmax_; found = true; }
+      if (!found && finite) {                                   // tier 1: moment bracket
+        const float inv_n = 1.0f / (float)nfin;
+        const float mean = fsum * inv_n;
+        const float sd = sqrtf(fmaxf(fsq * inv_n - mean * mean, 0.f));
+        const float lo = mean + (P.z_guess - P.win_sd) * sd, hi = mean + (P.z_guess + P.win_sd) * sd;
+        if (lo < hi && cfg.top_k <= nfin) found = bracket_select<NE, NT>(s, cfg.top_k, lo, hi, park, sm, &thr);
+      }
+      if (!found) {                                             // tiers 2 and 3 work on a copy: s[] stays in registers
+        float tmp[NE];
+#pragma unroll
+        for (int e = 0; e < NE; ++e) tmp[e] = s[e];
+        thr = select_slow<NE>(tmp, cfg.top_k, fmin_, fmax_, sm);
+      }
+      st.thr = thr;
     }
     // ---- softmax sum over the kept columns ----
     const ExpShift ex(m);
@@ -582,16 +626,32 @@ static int launch_all(const AcceptParams& P, cudaStream_t stream, int phases) {
   // rows up to 8192 columns: 256 threads x up to 32 elements (4 CTAs/SM); larger rows: 512 threads
   const int nt = c.ncols <= 8192 ? 256 : 512;
   const int nq = (nquads + nt - 1) / nt;
-  const int grid = (int)std::min<long long>(rows, (long long)kNumSMs * (nt == 256 ? 8 : 4));
-#define LAUNCH_STATS(NT, NQ) row_stats_kernel<DT, NT, NQ, VEC><<<grid, NT, 0, stream>>>(P)
+  int nq_inst = 1;
+  while (nq_inst < nq) nq_inst <<= 1;
+  if (nt == 512 && nq_inst < 8) nq_inst = 8;
+  const bool full = VEC && c.ncols == 4 * nt * nq_inst;
+  const int mode = full ? (P.mix.has_uncond ? 1 : 2) : 0;
+  const size_t park_bytes = (size_t)nq_inst * 4 * nt * sizeof(float);
+  const int per_sm = nq_inst <= 8 ? 1024 / nt : 512 / nt;
+  const int grid = (int)std::min<long long>(rows, (long long)kNumSMs * per_sm);
+#define LAUNCH_STATS(NT, NQ)                                                                              \
+  do {                                                                                                    \
+    auto k0 = row_stats_kernel<DT, NT, NQ, VEC, 0>;                                                       \
+    auto k1 = row_stats_kernel<DT, NT, NQ, true, 1>;                                                      \
+    auto k2 = row_stats_kernel<DT, NT, NQ, true, 2>;                                                      \
+    auto kk = mode == 1 ? k1 : (mode == 2 ? k2 : k0);                                                     \
+    if (park_bytes > 48 * 1024)                                                                           \
+      LANTERN_CUDA(cudaFuncSetAttribute(kk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)park_bytes)); \
+    kk<<<grid, NT, park_bytes, stream>>>(P);                                                              \
+  } while (0)
   if (!(phases & 1)) {
   } else if (nt == 256) {
-    if (nq <= 1) LAUNCH_STATS(256, 1);
-    else if (nq <= 2) LAUNCH_STATS(256, 2);
-    else if (nq <= 4) LAUNCH_STATS(256, 4);
+    if (nq_inst == 1) LAUNCH_STATS(256, 1);
+    else if (nq_inst == 2) LAUNCH_STATS(256, 2);
+    else if (nq_inst == 4) LAUNCH_STATS(256, 4);
     else LAUNCH_STATS(256, 8);
-  } else if (nq <= 8) LAUNCH_STATS(512, 8);
-  else if (nq <= 16) LAUNCH_STATS(512, 16);
+  } else if (nq_inst == 8) LAUNCH_STATS(512, 8);
+  else if (nq_inst == 16) LAUNCH_STATS(512, 16);
   else {
     set_error("ncols=%d exceeds the register-resident row limit (%d)", c.ncols, 16 * 4 * 512);
     return LANTERN_E_UNSUPPORTED;
@@ -709,7 +769,7 @@ extern "C" int lantern_accept_phases(const lantern_accept_cfg* cfg, const lanter
   P.do_topk = cfg->top_k > 0 && cfg->top_k < cfg->ncols;
   P.do_topp = 0;
   P.z_guess = P.do_topk ? (float)norm_ppf(1.0 - (double)cfg->top_k / (double)cfg->ncols) : 0.f;
-  P.win_sd = 0.15f;
+  P.win_sd = 0.2f;
   P.tail_raw = cfg->family == LANTERN_FAMILY_VANILLA;
   P.lumina = cfg->family == LANTERN_FAMILY_LUMINA;
   P.static_zero_q = cfg->static_tree && cfg->family != LANTERN_FAMILY_LUMINA;

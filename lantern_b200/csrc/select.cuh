@@ -1,16 +1,18 @@
 // Exact top-k threshold of a register-resident row (k-th largest value, duplicates counted), built for a
-// bandwidth-bound kernel: no per-element shared-memory atomics, a handful of ALU ops per element per pass.
+// bandwidth-bound kernel: a handful of ALU ops per element, no per-element shared-memory atomics.
 //
-//   1. One statistics pass gives finite-count / mean / variance / min / max of the row.
-//   2. A monotone 16-field classifier f(v) = clamp(round(v*scale + bias), 0, 15) splits the row into value-ordered
-//      fields; every thread counts its elements per field in nibble-packed registers, the block reduces the 16
-//      counts (REDUX + one shared-memory hop) and picks the field F holding the k-th largest element.
-//      The first classifier brackets the moment estimate mean + z_k*sd with 14 narrow interior fields, so F
-//      normally holds a few hundred candidates after ONE pass; otherwise the range is reset to the exact
-//      [min, max] of field F and the pass repeats (any monotone classifier keeps the search exact).
-//   3. The <= kListMax candidates of field F are compacted into shared memory and ranked exactly.
-//   4. If the statistics are not finite or the refinement does not converge, an MSB radix select over the
-//      ordered integer keys (shared-memory histograms) finishes the job; it is exact for every input.
+// Tier 1 (bracket_select) - the common case, one pass over the registers:
+//   * the caller's row statistics give the moment estimate mean + z_k*sd of the k-th largest value; a bracket
+//     [lo, hi] of +-win_sd standard deviations is placed around it;
+//   * every thread counts its elements above hi and parks its elements inside the bracket (a few per cent of
+//     the row) in a thread-private, conflict-free shared-memory column;
+//   * if the bracket really contains the k-th largest element (checked with the exact counts), the parked
+//     elements are histogrammed into 64 value-ordered fields (a few hundred shared-memory atomics per row), the
+//     field F holding the target is found with a warp scan, its handful of members is compacted and ranked.
+// Tier 2 (select_kth_largest) - bracket missed (non-Gaussian rows, heavy ties): 16-field classification of all
+//   register-resident elements with nibble-packed counters, range refinement on the exact [min, max] of the
+//   selected field until it holds <= kListMax candidates.  Any monotone classifier keeps the search exact.
+// Tier 3 - statistics not finite or no convergence: MSB radix select over ordered integer keys (caller).
 #pragma once
 
 #include "common.cuh"
@@ -24,17 +26,16 @@ struct SelectSmem {
   unsigned warp_cnt[32][8];   // per-warp field counts, two 16-bit fields per word
   unsigned total[16];
   float list[kListMax];
-  int rank_gt[kListMax];
-  int rank_ge[kListMax];
   float f4[4][33];            // float reductions
   unsigned hist[258];         // radix fallback
+  unsigned hist64[64];        // tier-1 fine histogram
   int i_scr[8];
   float f_scr[8];
 };
 
 // MSB-first radix select on ordered keys (exact for any input); returns the k-th largest key.
 template <int NE>
-__device__ __noinline__ uint32_t radix_select_kth(const float (&s)[NE], int k, unsigned* hist /*[258]*/) {
+__device__ __forceinline__ uint32_t radix_select_kth(const float (&s)[NE], int k, unsigned* hist /*[258]*/) {
   uint32_t prefix = 0, mask = 0;
   int krem = k;
   const int tid = threadIdx.x;
@@ -149,17 +150,128 @@ __device__ __forceinline__ void count_fields(const float (&s)[NE], const Classif
   __syncthreads();
 }
 
+// Exact krem-th largest (1-based) of sm.list[0..m): one warp per candidate, lanes split the comparisons.
+__device__ __forceinline__ float rank_list(int m, int krem, SelectSmem& sm) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+  for (int i = warp; i < m; i += nwarp) {
+    const float vi = sm.list[i];
+    int gt = 0, ge = 0;
+    for (int j = lane; j < m; j += 32) {
+      const float vj = sm.list[j];
+      gt += vj > vi;
+      ge += vj >= vi;
+    }
+    gt = __reduce_add_sync(0xffffffffu, gt);
+    ge = __reduce_add_sync(0xffffffffu, ge);
+    if (lane == 0 && gt < krem && krem <= ge) sm.f_scr[0] = vi;   // every qualifying candidate has the same value
+  }
+  __syncthreads();
+  return sm.f_scr[0];
+}
+
+struct Classifier64 {
+  float scale, bias23;   // field = clamp(round((v - lo) * 61 / (hi - lo)) + 1, 0, 63)
+  __device__ __forceinline__ unsigned operator()(float v) const {
+    float t = fmaf(v, scale, bias23);
+    t = fminf(fmaxf(t, 8388608.0f), 8388671.0f);
+    return __float_as_uint(t) & 63u;
+  }
+};
+__device__ __forceinline__ Classifier64 make_classifier64(float lo, float hi) {
+  Classifier64 c;
+  c.scale = 61.0f / (hi - lo);
+  c.bias23 = fmaf(-lo, c.scale, 1.0f) + 8388608.0f;
+  return c;
+}
+
+// Tier 1.  `buf` is a [NE][NT] float array in shared memory (column tid is private to the thread).
+// Returns true and sets *result when the k-th largest value was found.
+template <int NE, int NT>
+__device__ __forceinline__ bool bracket_select(const float (&s)[NE], int k, float lo, float hi, float* buf,
+                                               SelectSmem& sm, float* result) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  constexpr int NW = NT / 32;
+  int above = 0, slot = 0;
+#pragma unroll
+  for (int e = 0; e < NE; ++e) {
+    const float v = s[e];
+    const bool ab = v > hi;
+    above += ab;
+    if (!ab && v >= lo) {
+      buf[slot * NT + tid] = v;
+      ++slot;
+    }
+  }
+  // block totals of `above` and `slot`
+  const int wa = __reduce_add_sync(0xffffffffu, above), wi = __reduce_add_sync(0xffffffffu, slot);
+  __syncthreads();
+  if (lane == 0) { sm.warp_cnt[warp][0] = (unsigned)wa; sm.warp_cnt[warp][1] = (unsigned)wi; }
+  if (tid < 64) sm.hist64[tid] = 0u;
+  __syncthreads();
+  int tot_above = 0, tot_in = 0;
+#pragma unroll
+  for (int w = 0; w < NW; ++w) { tot_above += (int)sm.warp_cnt[w][0]; tot_in += (int)sm.warp_cnt[w][1]; }
+  if (!(tot_above < k && k <= tot_above + tot_in)) return false;   // the bracket missed the target
+  const int krem = k - tot_above;   // rank among the parked elements
+#pragma unroll 1
+  for (int it = 0; it < kSelMaxIters; ++it) {
+    const Classifier64 cls = make_classifier64(lo, hi);
+    if (!isfinite(cls.scale) || !isfinite(cls.bias23)) return false;
+    for (int i = 0; i < slot; ++i) atomicAdd(&sm.hist64[cls(buf[i * NT + tid])], 1u);
+    __syncthreads();
+    if (warp == 0) {
+      // lane l owns fields 2l, 2l+1; suffix sums from the top field down
+      const unsigned c0 = sm.hist64[2 * lane], c1 = sm.hist64[2 * lane + 1];
+      unsigned incl = c0 + c1;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const unsigned n = __shfl_down_sync(0xffffffffu, incl, o);
+        if (lane + o < 32) incl += n;
+      }
+      const unsigned above_pair = incl - (c0 + c1);     // elements in fields > 2l+1
+      if (above_pair < (unsigned)krem && above_pair + c1 >= (unsigned)krem) {
+        sm.i_scr[1] = 2 * lane + 1; sm.i_scr[2] = (int)above_pair; sm.i_scr[3] = (int)c1;
+      } else if (above_pair + c1 < (unsigned)krem && above_pair + c1 + c0 >= (unsigned)krem) {
+        sm.i_scr[1] = 2 * lane; sm.i_scr[2] = (int)(above_pair + c1); sm.i_scr[3] = (int)c0;
+      }
+      if (lane == 0) sm.i_scr[0] = 0;
+    }
+    __syncthreads();
+    const unsigned F = (unsigned)sm.i_scr[1];
+    const int above2 = sm.i_scr[2], cntF = sm.i_scr[3];
+    if (cntF <= kListMax) {
+      for (int i = 0; i < slot; ++i) {
+        const float v = buf[i * NT + tid];
+        if (cls(v) == F) sm.list[atomicAdd(&sm.i_scr[0], 1)] = v;
+      }
+      __syncthreads();
+      *result = rank_list(cntF, krem - above2, sm);
+      return true;
+    }
+    // too many candidates (ties / dense bracket): shrink to the exact [min, max] of field F and repeat
+    float mn = INFINITY, mxv = -INFINITY;
+    for (int i = 0; i < slot; ++i) {
+      const float v = buf[i * NT + tid];
+      if (cls(v) == F) { mn = fminf(mn, v); mxv = fmaxf(mxv, v); }
+    }
+    mn = -block_reduce(-mn, OpMaxF(), -INFINITY, sm.f4[0]);
+    mxv = block_reduce(mxv, OpMaxF(), -INFINITY, sm.f4[1]);
+    if (mn == mxv) { *result = mn; return true; }
+    lo = mn; hi = mxv;
+    if (tid < 64) sm.hist64[tid] = 0u;
+    __syncthreads();
+  }
+  return false;
+}
+
 // k-th largest of the row held in s[] (NE per thread, padded slots = -inf), 1 <= k <= number of slots.
-// `z_guess` = inverse normal CDF of (1 - k/n), `win_sd` = half-width of the first bracket in standard deviations.
+// Tier 2: starts from the full [row_min, row_max] range.  Returns false when it cannot converge (tier 3 needed).
 template <int NE>
-__device__ __forceinline__ float select_kth_largest(const float (&s)[NE], int k, float row_min, float row_max,
-                                                    float mean, float sd, float z_guess, float win_sd,
-                                                    SelectSmem& sm) {
+__device__ __forceinline__ bool select_kth_largest(const float (&s)[NE], int k, float row_min, float row_max,
+                                                SelectSmem& sm, float* out) {
   const int tid = threadIdx.x;
-  bool ok = isfinite(row_min) && isfinite(row_max) && isfinite(mean) && isfinite(sd);
-  float lo = fmaxf(mean + (z_guess - win_sd) * sd, row_min);
-  float hi = fminf(mean + (z_guess + win_sd) * sd, row_max);
-  if (!(lo < hi)) { lo = row_min; hi = row_max; }
+  bool ok = isfinite(row_min) && isfinite(row_max);
+  float lo = row_min, hi = row_max;
   float result = 0.f;
   bool done = false;
   if (ok && row_min == row_max) { result = row_max; done = true; }   // constant row (padding excluded by caller's k)
@@ -188,28 +300,8 @@ __device__ __forceinline__ float select_kth_largest(const float (&s)[NE], int k,
           if (cls(s[e]) == (unsigned)F) sm.list[atomicAdd(&sm.i_scr[0], 1)] = s[e];
         }
       }
-      const int m = (int)cntF;
-      int mp = 32;
-      while (mp < m) mp <<= 1;                 // power of two, <= kListMax <= blockDim.x
-      const int nparts = (int)blockDim.x / mp;  // threads sharing one candidate
-      const int ci = tid & (mp - 1), part = tid / mp;
-      for (int j = tid; j < kListMax; j += blockDim.x) { sm.rank_gt[j] = 0; sm.rank_ge[j] = 0; }
       __syncthreads();
-      if (ci < m) {
-        const float vi = sm.list[ci];
-        int gt = 0, ge = 0;
-        for (int j = part; j < m; j += nparts) {   // warp-uniform j: shared-memory broadcast
-          const float vj = sm.list[j];
-          gt += vj > vi;
-          ge += vj >= vi;
-        }
-        atomicAdd(&sm.rank_gt[ci], gt);
-        atomicAdd(&sm.rank_ge[ci], ge);
-      }
-      __syncthreads();
-      if (tid < m && sm.rank_gt[tid] < krem && krem <= sm.rank_ge[tid]) sm.f_scr[0] = sm.list[tid];  // same value from all writers
-      __syncthreads();
-      result = sm.f_scr[0];
+      result = rank_list((int)cntF, krem, sm);
       done = true;
     } else {
       // ---- too many candidates: shrink the range to the exact [min, max] of field F and classify again ----
@@ -225,8 +317,17 @@ __device__ __forceinline__ float select_kth_largest(const float (&s)[NE], int k,
       else { lo = mn; hi = mxv; }
     }
   }
-  if (!done) result = key_float(radix_select_kth<NE>(s, k, sm.hist));
-  return result;
+  *out = result;
+  return done;
+}
+
+// Tiers 2 + 3 behind one non-inlined call (rare path; works on the caller's copy of the row).
+template <int NE>
+__device__ __noinline__ float select_slow(const float (&s)[NE], int k, float row_min, float row_max, SelectSmem& sm) {
+  float r;
+  if (select_kth_largest<NE>(s, k, row_min, row_max, sm, &r)) return r;
+  __syncthreads();
+  return key_float(radix_select_kth<NE>(s, k, sm.hist));
 }
 
 }  // namespace lantern

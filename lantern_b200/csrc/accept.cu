@@ -17,6 +17,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 
 #include "common.cuh"
 #include "select.cuh"
@@ -50,7 +51,7 @@ struct AcceptParams {
   float win_sd;       // half-width of that bracket in standard deviations
 };
 
-constexpr int kWalkThreads = 512;
+constexpr int kWalkThreads = 1024;
 constexpr int kMaxSib = 64;
 
 __device__ __forceinline__ bool kept_col(float s, int idx, const RowStats& st) {
@@ -60,17 +61,27 @@ __device__ __forceinline__ bool kept_col(float s, int idx, const RowStats& st) {
 // ----------------------------------------------------------------------------------------------
 // Phase 1: per-row statistics
 // ----------------------------------------------------------------------------------------------
+template <int DT>
+__host__ __device__ constexpr int cfg_ncols_bytes(int ncols) { return ncols * Elem<DT>::kBytes; }
+
 // MODE 0: generic (bounds-checked, runtime CFG switch, -inf aware statistics).
 // MODE 1: fast path: vector loads, ncols == 4*NT*NQ exactly, CFG-mixed input (logits_uncond present).
 // MODE 2: fast path without logits_uncond.
 template <int DT, int NT, int NQ, bool VEC, int MODE>
-__global__ void __launch_bounds__(NT, (NQ <= 8 ? 1024 / NT : 512 / NT)) row_stats_kernel(const AcceptParams P) {
+__global__ void __launch_bounds__(NT, (MODE != 0 ? (NT <= 512 ? 2 : 1) : (NQ <= 8 ? 1024 / NT : 512 / NT)))
+    row_stats_kernel(const AcceptParams P) {
   constexpr int NE = NQ * 4;
   constexpr int NW = NT / 32;
   constexpr bool FAST = MODE != 0;
   __shared__ SelectSmem sm;
-  __shared__ double dscratch[33];
-  extern __shared__ __align__(16) float park[];   // [NE][NT] thread-private columns of the tier-1 select
+  __shared__ float fscratch[33];
+  __shared__ __align__(8) uint64_t mbar;
+  // dynamic shared memory: [staged cond row][staged uncond row] (fast modes) then the [NE][NT] parking columns
+  extern __shared__ __align__(128) unsigned char dyn_smem[];
+  const int stage_bytes = FAST ? ((cfg_ncols_bytes<DT>(P.cfg.ncols) + 32 + 127) & ~127) : 0;
+  unsigned char* buf_c = dyn_smem;
+  unsigned char* buf_u = dyn_smem + stage_bytes;
+  float* park = reinterpret_cast<float*>(dyn_smem + (MODE == 1 ? 2 : (MODE == 2 ? 1 : 0)) * stage_bytes);
 
   const lantern_accept_cfg& cfg = P.cfg;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -78,6 +89,34 @@ __global__ void __launch_bounds__(NT, (NQ <= 8 ? 1024 / NT : 512 / NT)) row_stat
   const bool has_uncond = MODE == 1 || (MODE == 0 && P.mix.has_uncond);
   MixParams mix = P.mix;
   mix.has_uncond = has_uncond;
+  constexpr int EB = Elem<DT>::kBytes;
+
+  // fast modes: single-buffer TMA pipeline.  Thread 0 issues the bulk copies of a row; the copy of row r+grid is
+  // issued as soon as row r has been lifted into registers, so it overlaps all of row r's arithmetic.
+  auto issue_row = [&](long long r) {
+    const int64_t rb = (r / cfg.n_rows) * cfg.item_stride + (r % cfg.n_rows) * cfg.row_stride + cfg.col0;
+    const uintptr_t gc = reinterpret_cast<uintptr_t>(P.in.logits_cond) + (uintptr_t)rb * EB;
+    const uintptr_t ac = gc & ~uintptr_t(15);
+    const uint32_t bc = (uint32_t)((gc - ac) + (uintptr_t)cfg.ncols * EB + 15) & ~15u;
+    uint32_t bu = 0;
+    uintptr_t au = 0;
+    if (MODE == 1) {
+      const uintptr_t gu = reinterpret_cast<uintptr_t>(P.in.logits_uncond) + (uintptr_t)rb * EB;
+      au = gu & ~uintptr_t(15);
+      bu = (uint32_t)((gu - au) + (uintptr_t)cfg.ncols * EB + 15) & ~15u;
+    }
+    mbar_expect_tx(&mbar, bc + bu);
+    bulk_g2s(buf_c, reinterpret_cast<const void*>(ac), bc, &mbar);
+    if (MODE == 1) bulk_g2s(buf_u, reinterpret_cast<const void*>(au), bu, &mbar);
+  };
+  uint32_t parity = 0;
+  if (FAST) {
+    if (tid == 0) {
+      mbar_init(&mbar, 1);
+      if ((long long)blockIdx.x < n_rows_total) issue_row(blockIdx.x);
+    }
+    __syncthreads();
+  }
 
   for (long long row = blockIdx.x; row < n_rows_total; row += gridDim.x) {
     const int b = (int)(row / cfg.n_rows), t = (int)(row % cfg.n_rows);
@@ -85,13 +124,13 @@ __global__ void __launch_bounds__(NT, (NQ <= 8 ? 1024 / NT : 512 / NT)) row_stat
     st.thr = -INFINITY; st.mx = 0.f; st.sum = 1.f; st.vcut = -INFINITY; st.icut = -1;
     st.kind = P.in.row_kinds ? (int)P.in.row_kinds[row] : LANTERN_ROW_IMAGE;
     st.pad0 = st.pad1 = 0;
-    if (st.kind != LANTERN_ROW_IMAGE) {   // one-hot rows: nothing to read
+    if (!FAST && st.kind != LANTERN_ROW_IMAGE) {   // one-hot rows: nothing to read
       if (tid == 0) P.stats[row] = st;
       continue;
     }
     const int64_t base = (int64_t)b * cfg.item_stride + (int64_t)t * cfg.row_stride + cfg.col0;
-    // pull the next row of this CTA towards L2 while this one is being processed
-    if (tid == 0 && row + gridDim.x < n_rows_total) {
+    // generic mode: pull the next row of this CTA towards L2 while this one is being processed
+    if (!FAST && tid == 0 && row + gridDim.x < n_rows_total) {
       const long long nr = row + gridDim.x;
       const int64_t nbase = (nr / cfg.n_rows) * cfg.item_stride + (nr % cfg.n_rows) * cfg.row_stride + cfg.col0;
       const size_t eb = Elem<DT>::kBytes;
@@ -105,14 +144,21 @@ __global__ void __launch_bounds__(NT, (NQ <= 8 ? 1024 / NT : 512 / NT)) row_stat
       }
     }
     float s[NE];
-    // ---- stream the row (fully unrolled: the loads are hoisted ahead of the arithmetic) ----
+    int lead_c = 0, lead_u = 0;   // bytes between the 16-byte aligned copy start and the first window element
+    if (FAST) {
+      lead_c = (int)((reinterpret_cast<uintptr_t>(P.in.logits_cond) + (uintptr_t)base * EB) & 15);
+      if (MODE == 1) lead_u = (int)((reinterpret_cast<uintptr_t>(P.in.logits_uncond) + (uintptr_t)base * EB) & 15);
+      mbar_wait(&mbar, parity);
+      parity ^= 1;
+    }
+    // ---- lift the row into registers (fully unrolled) ----
 #pragma unroll
     for (int q = 0; q < NQ; ++q) {
       const int e0 = (q * NT + tid) * 4;
       float c4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY}, u4[4] = {0.f, 0.f, 0.f, 0.f};
       if (FAST) {
-        Elem<DT>::load4(P.in.logits_cond, base + e0, c4);
-        if (MODE == 1) Elem<DT>::load4(P.in.logits_uncond, base + e0, u4);
+        lds4<DT>(buf_c + lead_c, e0, c4);
+        if (MODE == 1) lds4<DT>(buf_u + lead_u, e0, u4);
       } else if (VEC) {
         if (e0 < cfg.ncols) {
           Elem<DT>::load4(P.in.logits_cond, base + e0, c4);
@@ -129,6 +175,14 @@ __global__ void __launch_bounds__(NT, (NQ <= 8 ? 1024 / NT : 512 / NT)) row_stat
       }
 #pragma unroll
       for (int j = 0; j < 4; ++j) s[q * 4 + j] = mix_temper(c4[j], u4[j], mix);   // padding: -inf stays -inf
+    }
+    if (FAST) {
+      __syncthreads();   // every thread has consumed the staged row: the buffers may be overwritten
+      if (tid == 0 && row + gridDim.x < n_rows_total) issue_row(row + gridDim.x);
+      if (st.kind != LANTERN_ROW_IMAGE) {
+        if (tid == 0) P.stats[row] = st;
+        continue;
+      }
     }
     // ---- row statistics: sum, sum of squares, min, max (+ finite count), one fused two-level reduction ----
     float fsum = 0.f, fsq = 0.f, fmin_ = INFINITY, fmax_ = -INFINITY;
@@ -201,9 +255,8 @@ __global__ void __launch_bounds__(NT, (NQ <= 8 ? 1024 / NT : 512 / NT)) row_stat
       const float ev = ex(s[e]);           // padded / masked slots: ex2(-inf) = 0
       part += (s[e] >= st.thr) ? ev : 0.f;
     }
-    const double tot = block_reduce((double)part, OpSum(), 0.0, dscratch);
     st.mx = m;
-    st.sum = (float)tot;
+    st.sum = block_reduce(part, OpSum(), 0.f, fscratch);
     if (tid == 0) P.stats[row] = st;
   }
 }
@@ -325,8 +378,10 @@ __global__ void __launch_bounds__(kWalkThreads) walk_kernel(const AcceptParams P
   __syncthreads();
 
   // ---- distribution state: window S.p + one explicit out-of-window token + uniform remainder ----
+  // The residual is stored unnormalised: probability = stored value * scale.  A rejection then only zeroes
+  // entries and re-derives scale = 1 / sum instead of dividing the whole vector (reference: gtp /= gtp.sum()).
   int extra_tok = -1;
-  float p_extra = 0.f, p_out = 0.f;
+  float p_extra = 0.f, p_out = 0.f, scale = 1.0f;
   auto prob_of = [&](int tkn) -> float {
     if (tkn >= col0 && tkn < col1) return S.p[tkn - col0];
     if (tkn == extra_tok) return p_extra;
@@ -336,7 +391,7 @@ __global__ void __launch_bounds__(kWalkThreads) walk_kernel(const AcceptParams P
     const long long row = (long long)b * T + node;
     RowStats st = P.stats[row];
     __syncthreads();
-    extra_tok = -1; p_extra = 0.f; p_out = 0.f;
+    extra_tok = -1; p_extra = 0.f; p_out = 0.f; scale = 1.0f;
     if (st.kind != LANTERN_ROW_IMAGE) {
       for (int e = tid; e < ncols; e += NT) S.p[e] = 0.f;
       extra_tok = st.kind == LANTERN_ROW_NEWLINE ? cfg.newline_token : cfg.eoi_token;
@@ -389,13 +444,12 @@ __global__ void __launch_bounds__(kWalkThreads) walk_kernel(const AcceptParams P
       bool dup = false;
       for (int q = 0; q < ntried; ++q) dup |= (S.tried[q] == x);
       if (dup) continue;
-      __syncthreads();
-      if (tid == 0) S.tried[ntried] = x;
+      if (tid == 0) S.tried[ntried] = x;   // slot ntried is not read by the dup scan above
       ++ntried;
       __syncthreads();
 
       const float r = uniform(draws++);
-      float px = prob_of(x);
+      float px = __fmul_rn(prob_of(x), scale);
       bool relaxable = true;
       if (P.lumina) {
         if (is_syntax(x)) { px = 1.0f; relaxable = false; }
@@ -414,7 +468,7 @@ __global__ void __launch_bounds__(kWalkThreads) walk_kernel(const AcceptParams P
           if (tt < kk) v = (double)prob_of(__ldg(nb_row + tt) + off);
           double total;
           const double incl = carry + block_scan_incl(v, S.dscr, &total);
-          const float cs = (float)incl;
+          const float cs = (float)(incl * (double)scale);
           const bool ok = (tt < kk) && (cs <= bound);
           const int chunk = min(NT, kk - base_t);
           const int cnt = block_reduce(ok ? 1 : 0, OpSum(), 0, S.iscr);
@@ -488,13 +542,15 @@ __global__ void __launch_bounds__(kWalkThreads) walk_kernel(const AcceptParams P
           float qv = is_sib(tkn) ? 0.f : q[tkn];
           if (s1 > s0) qv = __fdiv_rn(qv, qsum);
           if (use_mask && ((S.nbmask[e >> 5] >> (e & 31)) & 1u)) qv = 0.f;
-          S.p[e] = fmaxf(__fsub_rn(S.p[e], qv), 0.f);
+          S.p[e] = fmaxf(__fsub_rn(__fmul_rn(S.p[e], scale), qv), 0.f);
         }
         if (extra_tok >= 0) {
           float qv = is_sib(extra_tok) ? 0.f : q[extra_tok];
           if (s1 > s0) qv = __fdiv_rn(qv, qsum);
-          p_extra = fmaxf(__fsub_rn(p_extra, qv), 0.f);
+          p_extra = fmaxf(__fsub_rn(__fmul_rn(p_extra, scale), qv), 0.f);
         }
+        p_out = __fmul_rn(p_out, scale);
+        scale = 1.0f;   // the subtraction pass stored normalised values
       } else {
         if (zero_nb) {
           for (int tt = tid; tt < kk1; tt += NT) {
@@ -506,22 +562,18 @@ __global__ void __launch_bounds__(kWalkThreads) walk_kernel(const AcceptParams P
         else if (x == extra_tok) p_extra = 0.f;
       }
       __syncthreads();
-      double part = 0.0;
-      for (int e = tid; e < ncols; e += NT) part += (double)S.p[e];
-      double tot = block_reduce(part, OpSum(), 0.0, S.dscr);
+      float part = 0.f;
+      for (int e = tid; e < ncols; e += NT) part += S.p[e];
+      double tot = block_reduce((double)part, OpSum(), 0.0, S.dscr);
       tot += (double)p_extra + (double)p_out * (double)(V - ncols - (extra_tok >= 0 ? 1 : 0));
-      float ssum = (float)tot;
-      if (ssum == 0.f) {   // gtp = ones_like(gtp)
+      if ((float)tot == 0.f) {   // gtp = ones_like(gtp)
         for (int e = tid; e < ncols; e += NT) S.p[e] = 1.0f;
         if (extra_tok >= 0) p_extra = 1.0f;
         p_out = 1.0f;
-        ssum = (float)V;
+        tot = (double)V;
         out_flags |= LANTERN_OUT_UNIFORM_FALLBACK;
-        __syncthreads();
       }
-      for (int e = tid; e < ncols; e += NT) S.p[e] = __fdiv_rn(S.p[e], ssum);
-      p_extra = __fdiv_rn(p_extra, ssum);
-      p_out = __fdiv_rn(p_out, ssum);
+      scale = __fdiv_rn(1.0f, (float)tot);   // gtp /= gtp.sum(), applied lazily
       adjust = true;
       __syncthreads();
     }
@@ -598,7 +650,7 @@ __global__ void __launch_bounds__(kWalkThreads) walk_kernel(const AcceptParams P
   }
   if (P.out.sample_p) {
     float* sp = P.out.sample_p + (size_t)b * V;
-    for (int v = tid; v < V; v += NT) sp[v] = prob_of(v);
+    for (int v = tid; v < V; v += NT) sp[v] = __fmul_rn(prob_of(v), scale);
   }
 }
 
@@ -623,28 +675,67 @@ static int launch_all(const AcceptParams& P, cudaStream_t stream, int phases) {
   const lantern_accept_cfg& c = P.cfg;
   const long long rows = (long long)c.n_items * c.n_rows;
   const int nquads = (c.ncols + 3) / 4;
-  // rows up to 8192 columns: 256 threads x up to 32 elements (4 CTAs/SM); larger rows: 512 threads
-  const int nt = c.ncols <= 8192 ? 256 : 512;
-  const int nq = (nquads + nt - 1) / nt;
-  int nq_inst = 1;
-  while (nq_inst < nq) nq_inst <<= 1;
-  if (nt == 512 && nq_inst < 8) nq_inst = 8;
-  const bool full = VEC && c.ncols == 4 * nt * nq_inst;
+  // Thread/element split.  Generic mode: 256 threads up to 8192 columns, 512 beyond.  Fast (TMA-staged) modes:
+  // 512 x 16 for 8192 columns (2 CTAs/SM), 1024 x 16 for 16384 (1 CTA/SM, the staged row pair fills shared memory).
+  constexpr int EB = Elem<DT>::kBytes;
+  const bool starts_aligned = ((size_t)c.col0 * EB) % 16 == 0 && ((size_t)c.row_stride * EB) % 16 == 0 &&
+                              ((size_t)c.item_stride * EB) % 16 == 0 &&
+                              reinterpret_cast<uintptr_t>(P.in.logits_cond) % 16 == 0 &&
+                              reinterpret_cast<uintptr_t>(P.in.logits_uncond) % 16 == 0;
+  const bool stageable = VEC && (starts_aligned || c.col0 + c.ncols + 8 <= c.row_stride);
+  int nt = c.ncols <= 8192 ? 256 : 512, nq_inst = 1;
+  bool full = false;
+  static const int fast_shapes[][3] = {{2048, 256, 2}, {4096, 256, 4}, {8192, 512, 4}, {16384, 1024, 4}, {32768, 1024, 8}};
+  const char* env_nt = getenv("LANTERN_STATS_NT");
+  for (auto& fsz : fast_shapes) {
+    if (stageable && c.ncols == fsz[0]) { nt = fsz[1]; nq_inst = fsz[2]; full = true; }
+  }
+  if (full && env_nt && c.ncols % (4 * atoi(env_nt)) == 0) {   // tuning knob for experiments
+    nt = atoi(env_nt);
+    nq_inst = c.ncols / (4 * nt);
+  }
+  if (!full) {
+    const int nq = (nquads + nt - 1) / nt;
+    while (nq_inst < nq) nq_inst <<= 1;
+    if (nt == 512 && nq_inst < 8) nq_inst = 8;
+  }
   const int mode = full ? (P.mix.has_uncond ? 1 : 2) : 0;
-  const size_t park_bytes = (size_t)nq_inst * 4 * nt * sizeof(float);
-  const int per_sm = nq_inst <= 8 ? 1024 / nt : 512 / nt;
+  const size_t stage_bytes = mode ? (((size_t)c.ncols * EB + 32 + 127) & ~size_t(127)) : 0;
+  const size_t park_bytes = (size_t)nq_inst * 4 * nt * sizeof(float) + (mode == 1 ? 2 : (mode == 2 ? 1 : 0)) * stage_bytes;
+  if (park_bytes + 6 * 1024 > 227 * 1024) {
+    set_error("row statistics kernel needs %zu bytes of shared memory", park_bytes);
+    return LANTERN_E_UNSUPPORTED;
+  }
+  int per_sm = mode ? (nt <= 512 ? 2 : 1) : (nq_inst <= 8 ? 1024 / nt : 512 / nt);
+  per_sm = std::max(1, std::min<int>(per_sm, (int)((227 * 1024) / (park_bytes + 5 * 1024))));
   const int grid = (int)std::min<long long>(rows, (long long)kNumSMs * per_sm);
-#define LAUNCH_STATS(NT, NQ)                                                                              \
+#define LAUNCH_STATS_MODE(NT, NQ, V, M)                                                                   \
   do {                                                                                                    \
-    auto k0 = row_stats_kernel<DT, NT, NQ, VEC, 0>;                                                       \
-    auto k1 = row_stats_kernel<DT, NT, NQ, true, 1>;                                                      \
-    auto k2 = row_stats_kernel<DT, NT, NQ, true, 2>;                                                      \
-    auto kk = mode == 1 ? k1 : (mode == 2 ? k2 : k0);                                                     \
+    auto kk = row_stats_kernel<DT, NT, NQ, V, M>;                                                         \
     if (park_bytes > 48 * 1024)                                                                           \
       LANTERN_CUDA(cudaFuncSetAttribute(kk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)park_bytes)); \
     kk<<<grid, NT, park_bytes, stream>>>(P);                                                              \
   } while (0)
+#define LAUNCH_FAST(NT, NQ)                        \
+  do {                                             \
+    if (mode == 1) LAUNCH_STATS_MODE(NT, NQ, true, 1); \
+    else LAUNCH_STATS_MODE(NT, NQ, true, 2);       \
+  } while (0)
+#define LAUNCH_STATS(NT, NQ) LAUNCH_STATS_MODE(NT, NQ, VEC, 0)
   if (!(phases & 1)) {
+  } else if (mode) {
+    if (nt == 256 && nq_inst == 2) LAUNCH_FAST(256, 2);
+    else if (nt == 256 && nq_inst == 4) LAUNCH_FAST(256, 4);
+    else if (nt == 256 && nq_inst == 8) LAUNCH_FAST(256, 8);
+    else if (nt == 512 && nq_inst == 4) LAUNCH_FAST(512, 4);
+    else if (nt == 512 && nq_inst == 8) LAUNCH_FAST(512, 8);
+    else if (nt == 1024 && nq_inst == 2) LAUNCH_FAST(1024, 2);
+    else if (nt == 1024 && nq_inst == 4) LAUNCH_FAST(1024, 4);
+    else if (nt == 1024 && nq_inst == 8) LAUNCH_FAST(1024, 8);
+    else {
+      set_error("no fast row-statistics instantiation for %d threads x %d quads", nt, nq_inst);
+      return LANTERN_E_UNSUPPORTED;
+    }
   } else if (nt == 256) {
     if (nq_inst == 1) LAUNCH_STATS(256, 1);
     else if (nq_inst == 2) LAUNCH_STATS(256, 2);
@@ -656,6 +747,8 @@ static int launch_all(const AcceptParams& P, cudaStream_t stream, int phases) {
     set_error("ncols=%d exceeds the register-resident row limit (%d)", c.ncols, 16 * 4 * 512);
     return LANTERN_E_UNSUPPORTED;
   }
+#undef LAUNCH_FAST
+#undef LAUNCH_STATS_MODE
 #undef LAUNCH_STATS
   LANTERN_CUDA(cudaGetLastError());
   if (!(phases & 2)) return LANTERN_OK;

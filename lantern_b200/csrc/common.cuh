@@ -76,6 +76,59 @@ struct Elem<LANTERN_F16> {
   }
 };
 
+// 4-element reads of a row staged in shared memory (same element order as Elem<DT>::load4).
+template <int DT>
+__device__ __forceinline__ void lds4(const unsigned char* buf, int elem_off, float (&o)[4]) {
+  if (DT == LANTERN_F32) {
+    const float4 v = *reinterpret_cast<const float4*>(buf + (size_t)elem_off * 4);
+    o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w;
+  } else {
+    const uint2 v = *reinterpret_cast<const uint2*>(buf + (size_t)elem_off * 2);
+    if (DT == LANTERN_BF16) {
+      o[0] = __uint_as_float(v.x << 16);
+      o[1] = __uint_as_float(v.x & 0xffff0000u);
+      o[2] = __uint_as_float(v.y << 16);
+      o[3] = __uint_as_float(v.y & 0xffff0000u);
+    } else {
+      const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&v.x));
+      const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&v.y));
+      o[0] = a.x; o[1] = a.y; o[2] = b.x; o[3] = b.y;
+    }
+  }
+}
+
+// ----------------------------------------------------------------------------------------------
+// TMA 1-D bulk copy (cp.async.bulk) + mbarrier: the DMA engine streams the next logits row into shared
+// memory while the SM works on the current one.
+// ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst_smem)),
+               "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra LAB_DONE;\n"
+      "bra LAB_WAIT;\n"
+      "LAB_DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+
 // CFG mix + temperature, one separately rounded fp32 op per reference ATen kernel
 // (ea_model_llamagen.py:28: uncond + (cond - uncond) * scale; HF TemperatureLogitsWarper: scores / T).
 // The intrinsics forbid FMA contraction so the value is bit-identical to the reference arithmetic.
@@ -156,24 +209,27 @@ struct OpMaxI {
 };
 
 // Block-wide scan of doubles: returns this thread's inclusive prefix, *total gets the block sum.
+// `scratch` holds one double per warp (<= 32 warps).
 __device__ __forceinline__ double block_scan_incl(double v, double* scratch, double* total) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = (blockDim.x + 31) >> 5;
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) {
-    double n = __shfl_up_sync(0xffffffffu, v, o);
+    const double n = __shfl_up_sync(0xffffffffu, v, o);
     if (lane >= o) v += n;
   }
   __syncthreads();
   if (lane == 31) scratch[warp] = v;
   __syncthreads();
-  double pre = 0.0, tot = 0.0;
-  for (int w = 0; w < nwarp; ++w) {
-    double t = scratch[w];
-    if (w < warp) pre += t;
-    tot += t;
+  // every warp scans the warp totals itself (no second barrier)
+  double t = lane < nwarp ? scratch[lane] : 0.0;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const double n = __shfl_up_sync(0xffffffffu, t, o);
+    if (lane >= o) t += n;
   }
-  *total = tot;
-  return pre + v;
+  *total = __shfl_sync(0xffffffffu, t, nwarp - 1);
+  const double pre = __shfl_sync(0xffffffffu, t, warp > 0 ? warp - 1 : 0);
+  return (warp > 0 ? pre : 0.0) + v;
 }
 
 // ----------------------------------------------------------------------------------------------

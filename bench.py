@@ -54,6 +54,7 @@ def parse():
     ap.add_argument("--cpu-items", type=int, default=0, help="items in the CPU sample (0 = auto)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="plain launches instead of CUDA-graph replay")
     return ap.parse_args()
 
 
@@ -226,7 +227,7 @@ def workload_config(args, items):
             "prompts_per_gpu": items, "tree": f"EAGLE-2 dynamic, {args.total_tokens} nodes, depth {DEPTH[args.family]}",
             "cfg_scale": args.cfg, "top_k": args.top_k, "temperature": 1.0, "lantern_k": args.lantern_k,
             "lantern_delta": args.lantern_delta, "logits": args.logits_dtype,
-            "tokens_per_image": TOKENS_PER_IMAGE[args.family],
+            "tokens_per_image": TOKENS_PER_IMAGE[args.family], "launch": "plain" if getattr(args, "no_graph", False) else "cuda-graph replay",
             "l2_policy": "inputs larger than L2: a pool of distinct batches, each > 126 MB of live logits"}
 
 
@@ -275,27 +276,69 @@ def run_b200(args):
 
     for i in range(max(args.warmup, 3)):
         step(i)
+    torch.cuda.synchronize()
+    # One CUDA graph per input batch (both kernels of the step): replay removes the Python/ctypes launch overhead,
+    # which is comparable to the GPU time of a step.  --no-graph times plain launches instead.
+    graphs, graph_out, kgraphs = [], [], []
+    if not args.no_graph:
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for i in range(len(batches)):
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, stream=side):
+                    r = step(i)
+                graphs.append(g)
+                graph_out.append(r)
+                g1 = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g1, stream=side):
+                    step(i, phases=1)
+                kgraphs.append(g1)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+
+    def run(i):
+        if graphs:
+            graphs[i % len(graphs)].replay()
+            return graph_out[i % len(graphs)]
+        return step(i)
+
+    def run_stats(i):
+        if kgraphs:
+            kgraphs[i % len(kgraphs)].replay()
+        else:
+            step(i, phases=1)
+
+    for i in range(3):
+        run(i)
     barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     results = []
     with ClockSampler(local) as clocks:
         ev0.record()
         for i in range(args.steps):
-            results.append(step(i))
+            results.append(run(i))
         ev1.record()
         torch.cuda.synchronize()
         ms = ev0.elapsed_time(ev1)
-        # dominant kernel alone (row statistics), same inputs, events on the launching stream
+        # dominant kernel alone (row statistics), same inputs, events on the launching stream; long enough for
+        # the clock sampler to see the GPU under load
         for i in range(3):
-            step(i, phases=1)
+            run_stats(i)
         torch.cuda.synchronize()
+        n_k = max(args.steps, 200)
         k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         k0.record()
-        for i in range(args.steps):
-            step(i, phases=1)
+        for i in range(n_k):
+            run_stats(i)
         k1.record()
         torch.cuda.synchronize()
-        ms_stats = k0.elapsed_time(k1) / args.steps
+        ms_stats = k0.elapsed_time(k1) / n_k
+        t_end = time.time() + 1.0            # keep the device busy for ~1 s so the sampler gets >= 5 readings
+        while time.time() < t_end:
+            for i in range(50):
+                run_stats(i)
+            torch.cuda.synchronize()
     tokens = sum(int((r.accept_length.sum() + B).item()) for r in results)
     accept_mean = tokens / (args.steps * B)
 

@@ -20,43 +20,15 @@
 #include <cstdlib>
 
 #include "common.cuh"
+#include "accept_types.cuh"
 #include "select.cuh"
+#include "stats_fast.cuh"
 
 namespace lantern {
-
-struct RowStats {
-  float thr;   // top-k threshold on the tempered value (keep s >= thr); -inf = keep all
-  float mx;    // max of the tempered row
-  float sum;   // sum over kept columns of exp(s - mx)
-  float vcut;  // top-p: columns with (s, idx) <= (vcut, icut) are removed; -inf / -1 = none
-  int icut;
-  int kind;    // LANTERN_ROW_*
-  int pad0, pad1;
-};
-static_assert(sizeof(RowStats) == 32, "RowStats layout");
-
-struct AcceptParams {
-  lantern_accept_cfg cfg;
-  lantern_accept_in in;
-  lantern_accept_out out;
-  RowStats* stats;
-  MixParams mix;
-  int vec_ok;     // rows can be read with 4-element vector loads
-  int do_topk;    // 0 < top_k < ncols
-  int do_topp;
-  int tail_raw;   // vanilla: tail row softmax without the processors
-  int lumina;
-  int static_zero_q;  // static + relaxed rejection zeroes neighbours in q (LlamaGen/Anole) instead of gtp
-  float z_guess;      // inverse normal CDF of 1 - top_k/ncols: first bracket of the top-k select
-  float win_sd;       // half-width of that bracket in standard deviations
-};
 
 constexpr int kWalkThreads = 1024;
 constexpr int kMaxSib = 64;
 
-__device__ __forceinline__ bool kept_col(float s, int idx, const RowStats& st) {
-  return (s >= st.thr) && ((s > st.vcut) || (s == st.vcut && idx > st.icut));
-}
 
 // ----------------------------------------------------------------------------------------------
 // Phase 1: per-row statistics
@@ -269,9 +241,13 @@ struct WalkSmem {
   unsigned* nbmask;  // [ceil(ncols/32)] neighbour bitmap (static LlamaGen/Anole rejection)
   int* ri;           // [L*D]
   int* tok;          // [T]
-  int* tried;        // [L]
+  int* tried;        // [L] distinct child tokens of the current node, first-occurrence order (kid_x)
+  int* kid_j;        // [L] candidates row that first reaches each child
+  int* kid_node;     // [L] tree node of each child
+  float* csv;        // [kWalkThreads] per-thread cumulative sums of the current neighbour chunk
+  float* uni;        // [T + 1] this item's uniforms (supplied or Philox)
   int* sib;          // [kMaxSib] tokens of the rejected node's earlier siblings
-  unsigned char* eq; // [L]
+  int* pid;          // [D+1][L] prefix class of every row per level: smallest row with the same token prefix
   double* dscr;      // [34]
   float* fscr;       // [34]
   int* iscr;         // [40]
@@ -360,22 +336,56 @@ __global__ void __launch_bounds__(kWalkThreads) walk_kernel(const AcceptParams P
   S.ri = reinterpret_cast<int*>(smem_raw + o);              o += (size_t)((L * D + 3) & ~3) * 4;
   S.tok = reinterpret_cast<int*>(smem_raw + o);             o += (size_t)((T + 3) & ~3) * 4;
   S.tried = reinterpret_cast<int*>(smem_raw + o);           o += (size_t)((L + 3) & ~3) * 4;
+  S.kid_j = reinterpret_cast<int*>(smem_raw + o);           o += (size_t)((L + 3) & ~3) * 4;
+  S.kid_node = reinterpret_cast<int*>(smem_raw + o);        o += (size_t)((L + 3) & ~3) * 4;
+  S.csv = reinterpret_cast<float*>(smem_raw + o);           o += (size_t)kWalkThreads * 4;
+  S.uni = reinterpret_cast<float*>(smem_raw + o);           o += (size_t)((T + 4) & ~3) * 4;
   S.sib = reinterpret_cast<int*>(smem_raw + o);             o += kMaxSib * 4;
   S.fscr = reinterpret_cast<float*>(smem_raw + o);          o += 36 * 4;
   S.iscr = reinterpret_cast<int*>(smem_raw + o);            o += 40 * 4;
-  S.eq = smem_raw + o;
+  S.pid = reinterpret_cast<int*>(smem_raw + o);
 
   const int* ri_g = P.in.retrieve + (cfg.retrieve_shared ? 0 : (size_t)b * L * D);
   const int* tok_g = P.in.tree_tokens + (size_t)b * T;
   for (int i = tid; i < L * D; i += NT) S.ri[i] = ri_g[i];
   for (int i = tid; i < T; i += NT) S.tok[i] = tok_g[i];
+  // at most one draw per tree node plus the bonus token (SURVEY.md Appendix A "uniform budget")
+  for (int i = tid; i < T + 1; i += NT) {
+    float uv;
+    if (P.in.uniforms) uv = i < cfg.n_uniforms ? P.in.uniforms[(size_t)b * cfg.n_uniforms + i] : 0.f;
+    else uv = philox_uniform(cfg.philox_seed, cfg.philox_step, (uint32_t)b, (uint32_t)i);
+    S.uni[i] = uv;
+  }
   __syncthreads();
   auto cand = [&](int j, int i) -> int {
     const int n = S.ri[j * D + i];
     return n >= 0 ? S.tok[n] : -1;
   };
-  for (int j = tid; j < L; j += NT) S.eq[j] = (cand(j, 0) == cand(0, 0)) ? 1 : 0;
+  // Prefix classes (once per item): pid[i][j] = smallest row j' whose tokens cand[j', 0:i] equal cand[j, 0:i].
+  // The reference's `is_eq` at level i (ea_model_llamagen.py:721) is "pid[i][j] == pid[i][best]"; a row is the first
+  // to offer its token at level i (the `candidates_set` dedup) iff pid[i+1][j] == j.
+  for (int j = tid; j < L; j += NT) S.pid[j] = 0;
   __syncthreads();
+  {
+    const int lane = tid & 31, warp = tid >> 5, nwarp = NT >> 5;
+    for (int i = 0; i < D; ++i) {   // one warp per row: the lanes scan the earlier rows with a ballot
+      const int* cur = S.pid + (size_t)i * L;
+      int* nxt = S.pid + (size_t)(i + 1) * L;
+      for (int j = warp; j < L; j += nwarp) {
+        const int cj = cur[j], xj = cand(j, i);
+        int rep = j;
+        for (int jb = cj; jb < j; jb += 32) {
+          const int jj = jb + lane;
+          const bool hit = jj < j && cur[jj] == cj && cand(jj, i) == xj;
+          const unsigned m = __ballot_sync(0xffffffffu, hit);
+          if (m) { rep = jb + __ffs(m) - 1; break; }
+        }
+        if (lane == 0) nxt[j] = rep;
+      }
+      __syncthreads();
+    }
+  }
+  int cls_cur = S.pid[(size_t)1 * L + 0];   // rows whose root token equals row 0's
 
   // ---- distribution state: window S.p + one explicit out-of-window token + uniform remainder ----
   // The residual is stored unnormalised: probability = stored value * scale.  A rejection then only zeroes
@@ -407,10 +417,7 @@ __global__ void __launch_bounds__(kWalkThreads) walk_kernel(const AcceptParams P
     }
     __syncthreads();
   };
-  auto uniform = [&](int d) -> float {
-    if (P.in.uniforms) return P.in.uniforms[(size_t)b * cfg.n_uniforms + d];
-    return philox_uniform(cfg.philox_seed, cfg.philox_step, (uint32_t)b, (uint32_t)d);
-  };
+  auto uniform = [&](int d) -> float { return S.uni[min(d, T)]; };
   auto is_syntax = [&](int tkn) -> bool {
     for (int i = 0; i < cfg.n_syntax; ++i)
       if (cfg.syntax_tokens[i] == tkn) return true;
@@ -425,29 +432,46 @@ __global__ void __launch_bounds__(kWalkThreads) walk_kernel(const AcceptParams P
   for (int lvl = 1; lvl < D; ++lvl) {
     if (lvl != accept_length) break;
     adjust = false;
-    // fi = first row still matching the accepted prefix
-    int fi = L;
-    for (int j = tid; j < L; j += NT)
-      if (S.eq[j]) { fi = j; break; }
-    fi = block_reduce(fi, OpMinI(), L, S.iscr);
+    // Warp 0 lists the distinct children of the current node in row order (the reference's `candidates_set`
+    // dedup, ea_model_llamagen.py:728-739) and finds fi, the first row still matching the accepted prefix.
+    if (tid < 32) {
+      int n = 0;
+      const int* cls_l = S.pid + (size_t)lvl * L;
+      const int* cls_n = S.pid + (size_t)(lvl + 1) * L;
+      for (int jb = 0; jb < L; jb += 32) {
+        const int j = jb + tid;
+        int x = -1, cn = -1;
+        if (j < L && cls_l[j] == cls_cur && cls_n[j] == j) {
+          cn = S.ri[j * D + lvl];
+          x = cn >= 0 ? S.tok[cn] : -1;
+        }
+        const bool first = x != -1;
+        const unsigned mf = __ballot_sync(0xffffffffu, first);
+        if (first) {
+          const int pos = n + __popc(mf & ((1u << tid) - 1u));
+          S.tried[pos] = x; S.kid_j[pos] = j; S.kid_node[pos] = cn;
+        }
+        n += __popc(mf);
+      }
+      if (tid == 0) S.iscr[38] = n;
+    }
+    __syncthreads();
+    const int n_kids = S.iscr[38], fi = cls_cur;   // the class representative is its first row
+    if (cfg.lantern && tid < n_kids) {   // pull the children's neighbour-table rows towards L2 behind the row load
+      const int xk = S.tried[tid] - off;
+      if (xk >= 0 && xk < ncols) {
+        const uintptr_t a0 = (reinterpret_cast<uintptr_t>(P.in.nbr_table + (size_t)xk * cfg.table_cols) + 15) & ~uintptr_t(15);
+        const uintptr_t a1 = reinterpret_cast<uintptr_t>(P.in.nbr_table + (size_t)xk * cfg.table_cols + kk1) & ~uintptr_t(15);
+        if (a1 > a0) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a0), "r"((unsigned)(a1 - a0)));
+      }
+    }
     int node = S.ri[fi * D + lvl - 1];
     if (node < 0) node += T;
     set_distribution(node, false);
 
-    int ntried = 0;
     bool accepted = false;
-    for (int j = 0; j < L && !accepted; ++j) {
-      if (!S.eq[j]) continue;
-      const int cnode = S.ri[j * D + lvl];
-      const int x = cnode >= 0 ? S.tok[cnode] : -1;
-      if (x == -1) continue;
-      bool dup = false;
-      for (int q = 0; q < ntried; ++q) dup |= (S.tried[q] == x);
-      if (dup) continue;
-      if (tid == 0) S.tried[ntried] = x;   // slot ntried is not read by the dup scan above
-      ++ntried;
-      __syncthreads();
-
+    for (int c = 0; c < n_kids && !accepted; ++c) {
+      const int j = S.kid_j[c], cnode = S.kid_node[c], x = S.tried[c];
       const float r = uniform(draws++);
       float px = __fmul_rn(prob_of(x), scale);
       bool relaxable = true;
@@ -464,20 +488,25 @@ __global__ void __launch_bounds__(kWalkThreads) walk_kernel(const AcceptParams P
         int n_ok = 0;
         for (int base_t = 0; base_t < kk; base_t += NT) {
           const int tt = base_t + tid;
+          const int chunk = min(NT, kk - base_t);
+          if (tid == 0) S.iscr[39] = chunk;             // index (within the chunk) of the first sum above the bound
           double v = 0.0;
           if (tt < kk) v = (double)prob_of(__ldg(nb_row + tt) + off);
           double total;
           const double incl = carry + block_scan_incl(v, S.dscr, &total);
           const float cs = (float)(incl * (double)scale);
-          const bool ok = (tt < kk) && (cs <= bound);
-          const int chunk = min(NT, kk - base_t);
-          const int cnt = block_reduce(ok ? 1 : 0, OpSum(), 0, S.iscr);
-          if (cnt > 0 && tid == cnt - 1) S.fscr[35] = cs;   // cumsum at the last index within the bound
+          const bool ok = (tt >= kk) || (cs <= bound);   // sums are non-decreasing: ok is a prefix of the chunk
+          S.csv[tid] = cs;
+          const unsigned bal = __ballot_sync(0xffffffffu, ok);
+          if ((tid & 31) == 0 && bal != 0xffffffffu) atomicMin(&S.iscr[39], (tid & ~31) + __ffs(~bal) - 1);
+          __syncthreads();
+          const int cnt = S.iscr[39];
+          if (cnt > 0) S.fscr[35] = S.csv[cnt - 1];      // every thread stores the same value
           n_ok += cnt;
           carry += total;
+          __syncthreads();
           if (cnt < chunk) break;
         }
-        __syncthreads();
         if (n_ok > 0) {
           idx = n_ok - 1;
           px = __fadd_rn(px, S.fscr[35]);
@@ -490,9 +519,7 @@ __global__ void __launch_bounds__(kWalkThreads) walk_kernel(const AcceptParams P
       }
       const float acp = __fdiv_rn(px, qx);
       if (r <= acp) {
-        __syncthreads();
-        for (int jj = tid; jj < L; jj += NT)
-          if (S.eq[jj] && cand(jj, lvl) != x) S.eq[jj] = 0;
+        cls_cur = j;   // == pid[lvl + 1][j]: rows that continue with token x
         ++accept_length;
         best = j;
         accepted = true;
@@ -592,10 +619,22 @@ __global__ void __launch_bounds__(kWalkThreads) walk_kernel(const AcceptParams P
 
   // ---------------- bonus token: inverse CDF, fp64, index order ----------------
   const float u = uniform(draws++);
-  const int per = (ncols + NT - 1) / NT;
+  const int per = (((ncols + NT - 1) / NT) + 3) & ~3;   // contiguous, float4-aligned chunk per thread
   const int i0 = min(tid * per, ncols), i1 = min(i0 + per, ncols);
   double loc = 0.0;
-  for (int i = i0; i < i1; ++i) loc += (double)S.p[i];
+  int last_nz = -1;
+  for (int i = i0; i + 4 <= i1; i += 4) {
+    const float4 v = *reinterpret_cast<const float4*>(S.p + i);
+    loc += ((double)v.x + (double)v.y) + ((double)v.z + (double)v.w);
+    if (v.x > 0.f) last_nz = i;
+    if (v.y > 0.f) last_nz = i + 1;
+    if (v.z > 0.f) last_nz = i + 2;
+    if (v.w > 0.f) last_nz = i + 3;
+  }
+  for (int i = i0 + ((i1 - i0) & ~3); i < i1; ++i) {
+    loc += (double)S.p[i];
+    if (S.p[i] > 0.f) last_nz = i;
+  }
   double wtot;
   const double incl = block_scan_incl(loc, S.dscr, &wtot);
   const double massA = (double)p_out * (double)col0;
@@ -614,9 +653,7 @@ __global__ void __launch_bounds__(kWalkThreads) walk_kernel(const AcceptParams P
         if (run > target) { atomicMin(&S.iscr[36], i + col0); break; }
       }
     }
-    int last_nz = -1;
-    for (int i = i0; i < i1; ++i) if (S.p[i] > 0.f) last_nz = i + col0;
-    if (last_nz >= 0) atomicMax(&S.iscr[37], last_nz);
+    if (last_nz >= 0) atomicMax(&S.iscr[37], last_nz + col0);
   }
   __syncthreads();
   int token = S.iscr[36];
@@ -664,9 +701,11 @@ static size_t walk_smem_bytes(const lantern_accept_cfg& c) {
   o += 34 * 8;
   o += (size_t)((c.n_paths * c.depth + 3) & ~3) * 4;
   o += (size_t)((c.n_rows + 3) & ~3) * 4;
-  o += (size_t)((c.n_paths + 3) & ~3) * 4;
+  o += 3 * (size_t)((c.n_paths + 3) & ~3) * 4;
+  o += (size_t)kWalkThreads * 4;
+  o += (size_t)((c.n_rows + 4) & ~3) * 4;
   o += kMaxSib * 4 + 36 * 4 + 40 * 4;
-  o += (size_t)((c.n_paths + 15) & ~15);
+  o += (size_t)(c.depth + 1) * c.n_paths * 4 + 16;
   return o;
 }
 
@@ -676,7 +715,8 @@ static int launch_all(const AcceptParams& P, cudaStream_t stream, int phases) {
   const long long rows = (long long)c.n_items * c.n_rows;
   const int nquads = (c.ncols + 3) / 4;
   // Thread/element split.  Generic mode: 256 threads up to 8192 columns, 512 beyond.  Fast (TMA-staged) modes:
-  // 512 x 16 for 8192 columns (2 CTAs/SM), 1024 x 16 for 16384 (1 CTA/SM, the staged row pair fills shared memory).
+  // 32 elements per thread (256 threads for 8192 columns, 512 for 16384): measured faster than 16 per thread
+  // because the per-thread fixed cost of the reductions is amortised over twice the elements.
   constexpr int EB = Elem<DT>::kBytes;
   const bool starts_aligned = ((size_t)c.col0 * EB) % 16 == 0 && ((size_t)c.row_stride * EB) % 16 == 0 &&
                               ((size_t)c.item_stride * EB) % 16 == 0 &&
@@ -685,7 +725,7 @@ static int launch_all(const AcceptParams& P, cudaStream_t stream, int phases) {
   const bool stageable = VEC && (starts_aligned || c.col0 + c.ncols + 8 <= c.row_stride);
   int nt = c.ncols <= 8192 ? 256 : 512, nq_inst = 1;
   bool full = false;
-  static const int fast_shapes[][3] = {{2048, 256, 2}, {4096, 256, 4}, {8192, 512, 4}, {16384, 1024, 4}, {32768, 1024, 8}};
+  static const int fast_shapes[][3] = {{2048, 256, 2}, {4096, 256, 4}, {8192, 256, 8}, {16384, 512, 8}, {32768, 1024, 8}};
   const char* env_nt = getenv("LANTERN_STATS_NT");
   for (auto& fsz : fast_shapes) {
     if (stageable && c.ncols == fsz[0]) { nt = fsz[1]; nq_inst = fsz[2]; full = true; }
@@ -716,10 +756,17 @@ static int launch_all(const AcceptParams& P, cudaStream_t stream, int phases) {
       LANTERN_CUDA(cudaFuncSetAttribute(kk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)park_bytes)); \
     kk<<<grid, NT, park_bytes, stream>>>(P);                                                              \
   } while (0)
-#define LAUNCH_FAST(NT, NQ)                        \
-  do {                                             \
-    if (mode == 1) LAUNCH_STATS_MODE(NT, NQ, true, 1); \
-    else LAUNCH_STATS_MODE(NT, NQ, true, 2);       \
+#define LAUNCH_FAST_MODE(NT, NQ, M)                                                                        \
+  do {                                                                                                    \
+    auto kk = row_stats_fast_kernel<DT, NT, NQ, M>;                                                       \
+    if (park_bytes > 48 * 1024)                                                                           \
+      LANTERN_CUDA(cudaFuncSetAttribute(kk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)park_bytes)); \
+    kk<<<grid, NT, park_bytes, stream>>>(P);                                                              \
+  } while (0)
+#define LAUNCH_FAST(NT, NQ)                     \
+  do {                                          \
+    if (mode == 1) LAUNCH_FAST_MODE(NT, NQ, 1); \
+    else LAUNCH_FAST_MODE(NT, NQ, 2);           \
   } while (0)
 #define LAUNCH_STATS(NT, NQ) LAUNCH_STATS_MODE(NT, NQ, VEC, 0)
   if (!(phases & 1)) {
@@ -748,6 +795,7 @@ static int launch_all(const AcceptParams& P, cudaStream_t stream, int phases) {
     return LANTERN_E_UNSUPPORTED;
   }
 #undef LAUNCH_FAST
+#undef LAUNCH_FAST_MODE
 #undef LAUNCH_STATS_MODE
 #undef LAUNCH_STATS
   LANTERN_CUDA(cudaGetLastError());
@@ -863,6 +911,7 @@ extern "C" int lantern_accept_phases(const lantern_accept_cfg* cfg, const lanter
   P.do_topp = 0;
   P.z_guess = P.do_topk ? (float)norm_ppf(1.0 - (double)cfg->top_k / (double)cfg->ncols) : 0.f;
   P.win_sd = 0.2f;
+  if (const char* w = getenv("LANTERN_WIN_SD")) P.win_sd = (float)atof(w);   // tuning knob (any value keeps the select exact)
   P.tail_raw = cfg->family == LANTERN_FAMILY_VANILLA;
   P.lumina = cfg->family == LANTERN_FAMILY_LUMINA;
   P.static_zero_q = cfg->static_tree && cfg->family != LANTERN_FAMILY_LUMINA;

@@ -97,7 +97,7 @@ typedef struct lantern_accept_cfg {
   int32_t retrieve_shared; /* 1: one retrieve_indices [L,D] for all items (static tree) */
   int32_t n_uniforms;   /* row stride of `uniforms` (>= tried candidates + 1 bonus draw) */
   int32_t n_q_rows;     /* static: rows per item in draft_op (sum over levels of parent groups) */
-  int32_t reserved0;
+  int32_t bonus_uniform_last; /* 1: the bonus-token draw reads uniforms[b, n_uniforms-1] instead of the next unread one */
   uint64_t philox_seed; /* used when uniforms == NULL */
   uint64_t philox_step; /* verify-step counter of the device Philox stream */
 } lantern_accept_cfg;

@@ -36,7 +36,7 @@ class AcceptCfg(C.Structure):
         ("lantern_delta_m1", C.c_float), ("table_cols", C.c_int32), ("tok_offset", C.c_int32),
         ("n_syntax", C.c_int32), ("syntax_tokens", C.c_int32 * MAX_SYNTAX),
         ("newline_token", C.c_int32), ("eoi_token", C.c_int32), ("retrieve_shared", C.c_int32),
-        ("n_uniforms", C.c_int32), ("n_q_rows", C.c_int32), ("reserved0", C.c_int32),
+        ("n_uniforms", C.c_int32), ("n_q_rows", C.c_int32), ("bonus_uniform_last", C.c_int32),
         ("philox_seed", C.c_uint64), ("philox_step", C.c_uint64),
     ]
 

@@ -208,7 +208,7 @@ __global__ void __launch_bounds__(NT, (MODE != 0 ? (NT <= 512 ? 2 : 1) : (NQ <= 
         const float inv_n = 1.0f / (float)nfin;
         const float mean = fsum * inv_n;
         const float sd = sqrtf(fmaxf(fsq * inv_n - mean * mean, 0.f));
-        const float lo = mean + (P.z_guess - P.win_sd) * sd, hi = mean + (P.z_guess + P.win_sd) * sd;
+        const float lo = mean + (P.z_guess - P.win_sd_first) * sd, hi = mean + (P.z_guess + P.win_sd_first) * sd;
         if (lo < hi && cfg.top_k <= nfin) found = bracket_select<NE, NT>(s, cfg.top_k, lo, hi, park, sm, &thr);
       }
       if (!found) {                                             // tiers 2 and 3 work on a copy: s[] stays in registers
@@ -618,7 +618,10 @@ __global__ void __launch_bounds__(kWalkThreads) walk_kernel(const AcceptParams P
   __syncthreads();
 
   // ---------------- bonus token: inverse CDF, fp64, index order ----------------
-  const float u = uniform(draws++);
+  const float u = (cfg.bonus_uniform_last && P.in.uniforms)
+                      ? P.in.uniforms[(size_t)b * cfg.n_uniforms + cfg.n_uniforms - 1]
+                      : uniform(draws);
+  ++draws;
   const int per = (((ncols + NT - 1) / NT) + 3) & ~3;   // contiguous, float4-aligned chunk per thread
   const int i0 = min(tid * per, ncols), i1 = min(i0 + per, ncols);
   double loc = 0.0;
@@ -910,7 +913,8 @@ extern "C" int lantern_accept_phases(const lantern_accept_cfg* cfg, const lanter
   P.do_topk = cfg->top_k > 0 && cfg->top_k < cfg->ncols;
   P.do_topp = 0;
   P.z_guess = P.do_topk ? (float)norm_ppf(1.0 - (double)cfg->top_k / (double)cfg->ncols) : 0.f;
-  P.win_sd = 0.2f;
+  P.win_sd = 0.08f;
+  P.win_sd_first = 0.25f;
   if (const char* w = getenv("LANTERN_WIN_SD")) P.win_sd = (float)atof(w);   // tuning knob (any value keeps the select exact)
   P.tail_raw = cfg->family == LANTERN_FAMILY_VANILLA;
   P.lumina = cfg->family == LANTERN_FAMILY_LUMINA;

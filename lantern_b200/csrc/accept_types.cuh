@@ -29,7 +29,8 @@ struct AcceptParams {
   int lumina;
   int static_zero_q;  // static + relaxed rejection zeroes neighbours in q (LlamaGen/Anole) instead of gtp
   float z_guess;      // inverse normal CDF of 1 - top_k/ncols: first bracket of the top-k select
-  float win_sd;       // half-width of that bracket in standard deviations
+  float win_sd;       // half-width of the bracket in standard deviations once a CTA tracks the observed quantile
+  float win_sd_first; // half-width for a CTA's first row (Gaussian prior only)
 };
 
 

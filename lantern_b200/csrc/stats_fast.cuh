@@ -66,6 +66,10 @@ __global__ void __launch_bounds__(NT, (NT <= 512 ? 2 : 1)) row_stats_fast_kernel
     if (MODE == 1) bulk_g2s(buf_u, reinterpret_cast<const void*>(au), bu, &fs.mbar);
   };
 
+  // Bracket centre in standard deviations: starts at the Gaussian quantile and then tracks the quantile observed on
+  // the CTA's previous row (rows of one model share their shape), so a narrow bracket keeps hitting on
+  // non-Gaussian logits; any miss is still resolved exactly by tiers 2/3.
+  float z_run = P.z_guess, win_run = P.win_sd_first;
   uint32_t parity = 0;
   // (item, t) of the current row and of the next row of this CTA, advanced without divisions
   int item = (int)blockIdx.x / cfg.n_rows, trow = (int)blockIdx.x % cfg.n_rows;
@@ -144,7 +148,7 @@ __global__ void __launch_bounds__(NT, (NT <= 512 ? 2 : 1)) row_stats_fast_kernel
         const float inv_n = 1.0f / (float)cfg.ncols;
         const float mean = fsum * inv_n;
         const float sd = sqrtf(fmaxf(fsq * inv_n - mean * mean, 0.f));
-        const float lo = mean + (P.z_guess - P.win_sd) * sd, hi = mean + (P.z_guess + P.win_sd) * sd;
+        const float lo = mean + (z_run - win_run) * sd, hi = mean + (z_run + win_run) * sd;
         if (lo < hi) {
           // bracket pass: count elements above hi, park the elements inside [lo, hi] in the thread's column
           int above = 0, slot = 0;
@@ -239,6 +243,13 @@ __global__ void __launch_bounds__(NT, (NT <= 512 ? 2 : 1)) row_stats_fast_kernel
         for (int e = 0; e < NE; ++e) tmp[e] = s[e];
         thr = select_slow<NE>(tmp, cfg.top_k, fmn, fmx, sm);
         __syncthreads();
+      }
+      {   // remember where the quantile really was (in standard deviations) for the next row
+        const float inv_n = 1.0f / (float)cfg.ncols;
+        const float mean = fsum * inv_n;
+        const float sd = sqrtf(fmaxf(fsq * inv_n - mean * mean, 0.f));
+        const float z_obs = (thr - mean) / sd;
+        if (isfinite(z_obs)) { z_run = z_obs; win_run = P.win_sd; }
       }
     }
 

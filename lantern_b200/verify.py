@@ -142,7 +142,7 @@ class Verifier:
              uniforms: Optional[torch.Tensor] = None, philox: Tuple[int, int] = (0, 0),
              node_q: Optional[torch.Tensor] = None, draft_op: Optional[torch.Tensor] = None,
              sib_tokens: Optional[torch.Tensor] = None, want_sample_p: bool = False,
-             phases: int = 3) -> VerifyResult:
+             phases: int = 3, bonus_uniform_last: bool = False) -> VerifyResult:
         """logits_*: [B, T, V] (fp32/bf16/fp16, last dim contiguous); tree_tokens: [B, T] int32;
         retrieve: [B, L, D] or [L, D] int32 (defaults to the static tree's).  Asynchronous."""
         if logits_cond.dim() != 3 or logits_cond.stride(2) != 1:
@@ -169,6 +169,7 @@ class Verifier:
                 raise ValueError("uniforms must be contiguous fp32 [B, n]")
             n_uni = uniforms.shape[1]
         cfg = self._cfg(B, T, L, D, logits_cond, shared, n_uni, philox)
+        cfg.bonus_uniform_last = int(bonus_uniform_last)
         ain = _abi.AcceptIn()
         ain.logits_cond, ain.logits_uncond = _ptr(logits_cond), _ptr(logits_uncond)
         ain.tree_tokens, ain.retrieve = _ptr(tree_tokens), _ptr(retrieve)

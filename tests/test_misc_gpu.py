@@ -1,0 +1,112 @@
+"""Neighbour-table build, host-buffer session and sweep edges on the GPU."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+import casegen as CG
+import cuda_runner as R
+from lantern_b200 import _abi, codebook, verify
+from oracle import lantern_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("N,d", [(64, 8), (512, 8), (1000, 8), (1024, 256), (4096, 8)])
+def test_neighbor_table_bit_exact(N, d):
+    rng = np.random.default_rng(N + d)
+    E = rng.standard_normal((N, d)).astype(np.float32)
+    E /= np.linalg.norm(E, axis=1, keepdims=True)
+    E[N // 2] = E[3]                                # exact duplicate rows -> distance ties broken by id
+    want = O.neighbor_table(E)
+    got = codebook.build_neighbor_table(torch.from_numpy(E).cuda()).cpu().numpy()
+    assert got.shape == (N, N - 1) and np.array_equal(got, want)
+    short = codebook.build_neighbor_table(torch.from_numpy(E).cuda(), k=17).cpu().numpy()
+    assert np.array_equal(short, want[:, :17])
+
+
+def test_reference_file_format_roundtrip(tmp_path):
+    E = torch.randn(256, 8, device="cuda")
+    t = codebook.build_neighbor_table(E)
+    path = codebook.save_reference_format(t, str(tmp_path))
+    raw = np.load(path)
+    assert path.endswith("top_255_indices.npy") and raw.dtype == np.uint16 and raw.shape == (256, 255)
+    back = codebook.load_neighbor_table(path, cols=11, device="cuda")
+    assert back.dtype == torch.int32 and torch.equal(back, t[:, :11])
+
+
+def _session_step(built, want_sample_p=False):
+    """Drive lantern_session_* with plain host (numpy) buffers."""
+    lib = _abi.load()
+    b0 = built[0]
+    p = b0.params
+    fam = R.family_spec(b0)
+    B, T = len(built), b0.tree.T
+    k = min(int(p["lantern_k"]), b0.fam.ncols - 1)
+    table = np.ascontiguousarray(b0.table.astype(np.int32))
+    ver = verify.Verifier(fam, temperature=p["temperature"], top_k=p["top_k"], cfg_scale=p["cfg_scale"], lantern=True,
+                          lantern_k=k, lantern_delta=p["lantern_delta"], nbr_table=torch.from_numpy(table).cuda())
+    cond = np.ascontiguousarray(np.stack([c.cond for c in built]))
+    uncond = np.ascontiguousarray(np.stack([c.uncond for c in built]))
+    tokens = np.ascontiguousarray(np.stack([c.tree.tokens for c in built]).astype(np.int32))
+    ri = R.pad_retrieve([c.tree.retrieve_indices for c in built])
+    uni = np.ascontiguousarray(np.stack([c.uniforms for c in built]).astype(np.float32))
+    L, D = ri.shape[1:]
+    cfg = ver._cfg(B, T, L, D, torch.from_numpy(cond), False, uni.shape[1], (0, 0))
+    sess = C.c_void_p()
+    _abi.check(lib.lantern_session_create(C.byref(cfg), table.ctypes.data, table.shape[0], C.byref(sess)))
+    ain = _abi.AcceptIn()
+    ain.logits_cond, ain.logits_uncond = cond.ctypes.data, uncond.ctypes.data
+    ain.tree_tokens, ain.retrieve, ain.uniforms = tokens.ctypes.data, ri.ctypes.data, uni.ctypes.data
+    out = {n: np.zeros(B, dtype=np.int32) for n in ("accept_length", "best_candidate", "token", "n_draws", "flags")}
+    path, sel = np.zeros((B, D), dtype=np.int32), np.zeros((B, D), dtype=np.int32)
+    sp = np.zeros((B, fam.vocab), dtype=np.float32)
+    aout = _abi.AcceptOut()
+    for n in out:
+        setattr(aout, n, out[n].ctypes.data)
+    aout.path_tokens, aout.select_indices = path.ctypes.data, sel.ctypes.data
+    if want_sample_p:
+        aout.sample_p = sp.ctypes.data
+    for _ in range(2):                                   # second step reuses the session's buffers
+        _abi.check(lib.lantern_session_step(sess, C.byref(cfg), C.byref(ain), C.byref(aout)))
+    lib.lantern_session_destroy(sess)
+    return out, path, sel, sp
+
+
+@pytest.mark.parametrize("family,kw", [("llamagen", dict(ncols=4096, top_k=500, boost=11.0)),
+                                       ("anole", dict(ncols=2048, top_k=400, boost=11.0)),
+                                       ("lumina_mgpt", dict())])
+def test_host_buffer_session_matches_oracle(family, kw):
+    built, orcs, seed = [], [], 12000
+    while len(built) < 5:
+        b = CG.build(dict(family=family, seed=seed, depth=5 if family == "lumina_mgpt" else 4, **kw))
+        seed += 1
+        o = CG.oracle_step(b)
+        if o.margin >= 1e-5:
+            built.append(b)
+            orcs.append(o)
+    out, path, sel, sp = _session_step(built, want_sample_p=True)
+    for i, o in enumerate(orcs):
+        a = int(out["accept_length"][i])
+        assert a == o.accept_length and int(out["best_candidate"][i]) == o.best_candidate
+        assert int(out["token"][i]) == o.token and int(out["n_draws"][i]) == o.n_uniforms
+        assert path[i, :a + 1].tolist() == o.accepted_tokens.tolist() and sel[i, :a + 1].tolist() == o.select_indices.tolist()
+        R.assert_probs_close(sp[i], o.sample_p)
+
+
+@pytest.mark.parametrize("B,T", [(1, 1), (3, 2), (2, 33), (17, 59), (5, 256)])
+def test_accept_sweep_shapes(B, T):
+    """BASELINE configs[4]: tree 1-256 x batch sizes; every item equals its own oracle."""
+    built, orcs, seed = [], [], 20000 + 10 * T
+    while len(built) < B:
+        b = CG.build(dict(family="llamagen", ncols=2048, tree="random", total_tokens=T, top_k=300, lantern_k=100,
+                          boost=10.0, seed=seed))
+        seed += 1
+        o = CG.oracle_step(b)
+        if o.margin >= 1e-5:
+            built.append(b)
+            orcs.append(o)
+    res = R.run_cases(built)
+    for i, o in enumerate(orcs):
+        R.compare(res, i, o)

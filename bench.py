@@ -400,7 +400,7 @@ def run_b200(args):
             line["e2e"] = {"value": e2e["tokens"] / (e2e["ms"] * 1e-3) / tpi, "unit": "images/s",
                            "h2d_bytes_per_step": e2e["h2d"], "d2h_bytes_per_step": e2e["d2h"],
                            "ms_per_step": e2e["ms"] / e2e["steps"], "steps": e2e["steps"]}
-        if not args.no_cpu and world >= 1:
+        if not args.no_cpu and world == 1:
             cores = os.cpu_count() or 1
             n_items = args.cpu_items or max(cores, 16)
             v, st, tok, wall = cpu_reference(args, n_items, 2, cores)

@@ -23,6 +23,7 @@
 #include "accept_types.cuh"
 #include "select.cuh"
 #include "stats_fast.cuh"
+#include "topp.cuh"
 
 namespace lantern {
 
@@ -802,6 +803,10 @@ static int launch_all(const AcceptParams& P, cudaStream_t stream, int phases) {
 #undef LAUNCH_STATS_MODE
 #undef LAUNCH_STATS
   LANTERN_CUDA(cudaGetLastError());
+  if ((phases & 1) && P.do_topp) {   // nucleus cut on top of the row statistics (slow path, one CTA per row)
+    row_topp_kernel<DT, VEC><<<(unsigned)rows, kToppThreads, 0, stream>>>(P);
+    LANTERN_CUDA(cudaGetLastError());
+  }
   if (!(phases & 2)) return LANTERN_OK;
   const size_t smem = walk_smem_bytes(c);
   if (smem > 227 * 1024) {
@@ -892,10 +897,6 @@ extern "C" int lantern_accept_phases(const lantern_accept_cfg* cfg, const lanter
   }
   int rc = validate(*cfg, *in, *out);
   if (rc) return rc;
-  if (1e-8f <= cfg->top_p && cfg->top_p < 1.0f) {
-    set_error("lantern_accept_fused: top_p < 1 is not implemented in the fused kernel yet");
-    return LANTERN_E_UNSUPPORTED;
-  }
   if (!workspace_dev || workspace_bytes < lantern_accept_workspace_bytes(cfg)) {
     set_error("lantern_accept_fused: workspace too small (%zu < %zu)", workspace_bytes,
               lantern_accept_workspace_bytes(cfg));
@@ -911,7 +912,7 @@ extern "C" int lantern_accept_phases(const lantern_accept_cfg* cfg, const lanter
   P.mix.has_uncond = in->logits_uncond != nullptr;
   P.mix.do_temp = cfg->temperature != 1.0f;
   P.do_topk = cfg->top_k > 0 && cfg->top_k < cfg->ncols;
-  P.do_topp = 0;
+  P.do_topp = (1e-8f <= cfg->top_p && cfg->top_p < 1.0f) ? 1 : 0;
   P.z_guess = P.do_topk ? (float)norm_ppf(1.0 - (double)cfg->top_k / (double)cfg->ncols) : 0.f;
   P.win_sd = 0.08f;
   P.win_sd_first = 0.25f;

@@ -24,7 +24,7 @@ def _id(c):
 
 
 def _supported(p):
-    return not (1e-8 <= p["top_p"] < 1.0)
+    return True
 
 
 @pytest.mark.parametrize("case", [c for c in GOLD["cases"] if _supported(c["params"])], ids=_id)
@@ -162,13 +162,35 @@ def test_topk_ties_and_constant_rows():
 
 def test_error_paths():
     from lantern_b200 import _abi, verify
-    b = C.build(dict(family="llamagen", ncols=1024, top_k=100, lantern=False, seed=1))
-    v = verify.Verifier(verify.LLAMAGEN.resized(1024), top_k=100, top_p=0.5)
-    cond = torch.from_numpy(b.cond[None]).cuda()
-    tok = torch.from_numpy(b.tree.tokens[None].astype(np.int32)).cuda()
-    ri = torch.from_numpy(b.tree.retrieve_indices[None].astype(np.int32)).cuda()
+    V = 65536                                               # wider than the register-resident row limit (32768)
+    v = verify.Verifier(verify.vanilla(V), top_k=100)
+    cond = torch.zeros(1, 2, V, device="cuda")
+    tok = torch.zeros(1, 2, dtype=torch.int32, device="cuda")
+    ri = torch.tensor([[[0, 1]]], dtype=torch.int32, device="cuda")
     with pytest.raises(_abi.LanternError) as e:
         v.step(cond, None, tok, ri)
     assert e.value.code == _abi.E_UNSUPPORTED
     with pytest.raises(ValueError):
         verify.Verifier(verify.LLAMAGEN, lantern=True)      # no table
+    with pytest.raises(ValueError):
+        verify.Verifier(verify.LLAMAGEN, temperature=0.0)   # greedy has no sampling walk
+
+
+@pytest.mark.parametrize("top_p,top_k,temp", [(0.9, 0, 1.0), (0.5, 300, 1.0), (0.95, 2000, 0.8), (0.3, 0, 1.3)])
+def test_top_p(top_p, top_k, temp):
+    """HF order Temperature -> TopP -> TopK (drafters/utils.py:43-51), ties at the nucleus boundary by column."""
+    built, orcs, seed = [], [], 31000
+    while len(built) < 6:
+        b = C.build(dict(family="llamagen", seed=seed, ncols=4096, top_p=top_p, top_k=top_k, temperature=temp,
+                         lantern_k=50, boost=11.0))
+        seed += 1
+        if seed % 2:
+            b.cond = np.round(b.cond * 4) / 4                # exact ties inside the row
+            b.uncond = np.round(b.uncond * 4) / 4
+        o = C.oracle_step(b)
+        if o.margin >= MARGIN:
+            built.append(b)
+            orcs.append(o)
+    res = R.run_cases(built)
+    for i, o in enumerate(orcs):
+        R.compare(res, i, o)

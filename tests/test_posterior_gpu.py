@@ -123,7 +123,7 @@ def _run_case(case, fused):
     return best, a, sample_p, orc, u, case
 
 
-SUPPORTED = lambda p: not (1e-8 <= p["top_p"] < 1.0)
+SUPPORTED = lambda p: True
 
 
 @pytest.mark.parametrize("fused", [False, True])

@@ -189,11 +189,20 @@ LANTERN_API int lantern_kv_compact(const lantern_kv_cfg* cfg, void* const* slab_
 /*
  * Neighbour-table build (entrypoints/generate_codebook.py:53-60): for every codebook row the ids of
  * its K nearest other rows, nearest first; order = (squared L2 distance in fp64, id).
- * E_dev: [N, d] fp32 row-major.  out_dev: [N, K] int32.  Synchronous workspace-free helper:
- * allocates and frees its own scratch.
+ * E_dev: [N, d] fp32 row-major.  out_dev: [N, K] int32.  Allocates and frees its own scratch (stream-ordered).
+ * For K <= N/2 the candidates come from a tcgen05 distance GEMM and are re-ranked exactly; otherwise (or if the
+ * GEMM's error bound is ever violated) every distance is computed in fp64.  Both routes give identical tables.
  */
 LANTERN_API int lantern_build_neighbors(const float* E_dev, int32_t N, int32_t d, int32_t K, int32_t* out_dev,
                             void* stream);
+
+/* Test hook of the tensor-core path of lantern_build_neighbors: the approximate squared-distance matrix
+ * D~[i][j] = |e_i|^2 + |e_j|^2 - 2 e_i.e_j (tcgen05, TF32 cross term), fp32 [N, ld], diagonal = +inf. */
+LANTERN_API int lantern_debug_dist_gemm(const float* E_dev, int32_t N, int32_t d, float* D_dev, int32_t ld, void* stream);
+
+/* Which route the last lantern_build_neighbors call on this thread took: 1 = tensor-core candidates + exact
+ * re-rank, 2 = all-fp64 kernel (test hook). */
+LANTERN_API int lantern_debug_neighbors_path(void);
 
 /* Host-side copy of the device Philox stream (for tests and for seeding the CPU oracle):
  * draw i of item `item` at step `step`, i in [0, n). */

@@ -5,6 +5,8 @@
 // all N rows are computed straight into shared memory from a transposed copy of the codebook (coalesced
 // reads), then the (distance, id) pairs are bitonic-sorted in shared memory and the first K ids written out.
 // The N x N distance matrix never touches HBM.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace lantern {
@@ -67,6 +69,12 @@ __global__ void __launch_bounds__(kNbrThreads) nbr_rows_kernel(const float* __re
 
 }  // namespace lantern
 
+static thread_local int g_last_path = 0;   // 1 = tensor-core candidates + exact re-rank, 2 = all-fp64 kernel
+
+extern "C" LANTERN_API int lantern_debug_neighbors_path(void) { return g_last_path; }
+
+int build_neighbors_tensor_core(const float* E_dev, int N, int d, int K, int32_t* out_dev, cudaStream_t s, int* fell_back);
+
 extern "C" int lantern_build_neighbors(const float* E_dev, int32_t N, int32_t d, int32_t K, int32_t* out_dev,
                                        void* stream) {
   using namespace lantern;
@@ -82,6 +90,13 @@ extern "C" int lantern_build_neighbors(const float* E_dev, int32_t N, int32_t d,
     return LANTERN_E_UNSUPPORTED;
   }
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (getenv("LANTERN_NBR_EXACT_ONLY") == nullptr) {   // tensor-core path for K << N (bit-identical results)
+    int fell_back = 1;
+    const int rc = build_neighbors_tensor_core(E_dev, N, d, K, out_dev, s, &fell_back);
+    if (rc != LANTERN_OK) return rc;
+    if (!fell_back) { g_last_path = 1; return LANTERN_OK; }
+  }
+  g_last_path = 2;
   float* Et = nullptr;
   LANTERN_CUDA(cudaMallocAsync(&Et, (size_t)N * d * sizeof(float), s));
   const int64_t n = (int64_t)N * d;

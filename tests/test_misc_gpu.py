@@ -110,3 +110,44 @@ def test_accept_sweep_shapes(B, T):
     res = R.run_cases(built)
     for i, o in enumerate(orcs):
         R.compare(res, i, o)
+
+
+@pytest.mark.parametrize("N,d", [(512, 8), (1000, 8), (1024, 256), (2048, 40)])
+def test_tensor_core_distance_gemm_within_bound(N, d):
+    """tcgen05 TF32 distance GEMM against fp64 distances: inside the error bound the exact re-rank relies on."""
+    lib = _abi.load()
+    rng = np.random.default_rng(N * 7 + d)
+    E = rng.standard_normal((N, d)).astype(np.float32)
+    E /= np.linalg.norm(E, axis=1, keepdims=True)
+    Ed = torch.from_numpy(E).cuda()
+    ld = (N + 3) & ~3
+    D = torch.full((N, ld), -1.0, device="cuda")
+    _abi.check(lib.lantern_debug_dist_gemm(Ed.data_ptr(), N, d, D.data_ptr(), ld, torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    got = D[:, :N].cpu().numpy().astype(np.float64)
+    E64 = E.astype(np.float64)
+    want = ((E64[:, None, :] - E64[None, :, :]) ** 2).sum(-1) if N <= 1024 else \
+        (E64 ** 2).sum(1)[:, None] + (E64 ** 2).sum(1)[None, :] - 2 * E64 @ E64.T
+    assert np.all(np.isinf(np.diag(got)))
+    off = ~np.eye(N, dtype=bool)
+    err = np.abs(got - want)[off].max()
+    assert err <= 1.5 * (0.0025 + 2 * 6e-5), f"max |D~ - d^2| = {err}"
+
+
+@pytest.mark.parametrize("N,d,K", [(4096, 8, 101), (2048, 256, 65), (8192, 8, 1001), (1000, 8, 33)])
+def test_tensor_core_neighbor_table_bit_exact(N, d, K):
+    rng = np.random.default_rng(N + d + K)
+    E = rng.standard_normal((N, d)).astype(np.float32)
+    E /= np.linalg.norm(E, axis=1, keepdims=True)
+    E[5] = E[N // 3]                                   # duplicate row: tie broken by id
+    want = O.neighbor_table(E, K)
+    got = codebook.build_neighbor_table(torch.from_numpy(E).cuda(), k=K).cpu().numpy()
+    assert _abi.load().lantern_debug_neighbors_path() == 1, "tensor-core path fell back to the fp64 kernel"
+    assert np.array_equal(got, want)
+    os_env = __import__("os").environ
+    os_env["LANTERN_NBR_EXACT_ONLY"] = "1"             # the all-fp64 route gives the same table
+    try:
+        exact = codebook.build_neighbor_table(torch.from_numpy(E).cuda(), k=K).cpu().numpy()
+    finally:
+        del os_env["LANTERN_NBR_EXACT_ONLY"]
+    assert np.array_equal(exact, want)

@@ -54,6 +54,7 @@ def parse():
     ap.add_argument("--cpu-items", type=int, default=0, help="items in the CPU sample (0 = auto)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-lazy", action="store_true", help="skip the lazy-statistics side measurement")
     ap.add_argument("--no-graph", action="store_true", help="plain launches instead of CUDA-graph replay")
     return ap.parse_args()
 
@@ -309,6 +310,22 @@ def run_b200(args):
         else:
             step(i, phases=1)
 
+    # lazy-statistics variant of the same step (phases = 6): measured beside the default, reported as "lazy_stats"
+    lazy_graphs = []
+    if not args.no_graph and not args.no_lazy:
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for i in range(len(batches)):
+                step(i, phases=6)
+            for i in range(len(batches)):
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, stream=side):
+                    r = step(i, phases=6)
+                lazy_graphs.append((g, r))
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+
     for i in range(3):
         run(i)
     barrier()
@@ -334,6 +351,20 @@ def run_b200(args):
         k1.record()
         torch.cuda.synchronize()
         ms_stats = k0.elapsed_time(k1) / n_k
+        ms_lazy, tokens_lazy = None, 0
+        if lazy_graphs:
+            for g, _ in lazy_graphs:
+                g.replay()
+            torch.cuda.synchronize()
+            l0, l1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            l0.record()
+            for i in range(args.steps):
+                lazy_graphs[i % len(lazy_graphs)][0].replay()
+            l1.record()
+            torch.cuda.synchronize()
+            ms_lazy = l0.elapsed_time(l1) / args.steps
+            tokens_lazy = sum(int((lazy_graphs[i % len(lazy_graphs)][1].accept_length.sum() + B).item())
+                              for i in range(args.steps))
         t_end = time.time() + 1.0            # keep the device busy for ~1 s so the sampler gets >= 5 readings
         while time.time() < t_end:
             for i in range(50):
@@ -396,6 +427,10 @@ def run_b200(args):
                          "bytes_per_launch": stat_bytes, "ms_per_launch": ms_stats,
                          "frac_of_nominal_8TBs": achieved / 8000.0},
         }
+        if ms_lazy is not None:
+            line["lazy_stats"] = {"ms_per_step": ms_lazy, "value": tokens_lazy / (ms_lazy * args.steps * 1e-3) / tpi,
+                                  "unit": "images/s (this rank)", "gpu_launches_per_step": 1,
+                                  "note": "phases=6: statistics only for the rows the walk visits (no streamed kernel)"}
         if e2e is not None:
             line["e2e"] = {"value": e2e["tokens"] / (e2e["ms"] * 1e-3) / tpi, "unit": "images/s",
                            "h2d_bytes_per_step": e2e["h2d"], "d2h_bytes_per_step": e2e["d2h"],

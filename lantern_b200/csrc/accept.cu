@@ -319,7 +319,91 @@ __device__ __forceinline__ RowStats raw_row_stats(const AcceptParams& P, int b, 
   return st;
 }
 
-template <int DT, bool VEC>
+// Lazy mode (phases bit 2): statistics of a visited row computed inside the walk CTA, straight from the logits,
+// and the probability vector written from registers (one global read of the row instead of two, and no
+// statistics for the ~85 % of tree rows the walk never visits).  Same arithmetic as the streamed kernels.
+template <int DT, int NE>
+__device__ __forceinline__ void lazy_probs(const AcceptParams& P, int b, int node, bool raw, float* p, float* park,
+                                           SelectSmem& sm, float* part_scr, float& z_run, float& win_run) {
+  constexpr int NT = kWalkThreads, NW = NT / 32, NQ = NE / 4;
+  const lantern_accept_cfg& cfg = P.cfg;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int64_t base = (int64_t)b * cfg.item_stride + (int64_t)node * cfg.row_stride + cfg.col0;
+  MixParams mix = P.mix;
+  if (raw) mix.do_temp = 0;
+  float s[NE];
+  float fsum = 0.f, fsq = 0.f, fmn = INFINITY, fmx = -INFINITY;
+#pragma unroll
+  for (int q = 0; q < NQ; ++q) {
+    const int e0 = (q * NT + tid) * 4;
+    float c4[4], u4[4] = {0.f, 0.f, 0.f, 0.f};
+    Elem<DT>::load4(P.in.logits_cond, base + e0, c4);
+    if (mix.has_uncond) Elem<DT>::load4(P.in.logits_uncond, base + e0, u4);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float v = mix_temper(c4[j], u4[j], mix);
+      s[q * 4 + j] = v;
+      fsum += v; fsq = fmaf(v, v, fsq); fmn = fminf(fmn, v); fmx = fmaxf(fmx, v);
+    }
+  }
+  fsum = warp_reduce(fsum, OpSum()); fsq = warp_reduce(fsq, OpSum());
+  fmn = -warp_reduce(-fmn, OpMaxF()); fmx = warp_reduce(fmx, OpMaxF());
+  __syncthreads();
+  if (lane == 0) { sm.f4[0][warp] = fsum; sm.f4[1][warp] = fsq; sm.f4[2][warp] = fmn; sm.f4[3][warp] = fmx; }
+  __syncthreads();
+  fsum = 0.f; fsq = 0.f; fmn = INFINITY; fmx = -INFINITY;
+#pragma unroll 8
+  for (int w = 0; w < NW; ++w) {
+    fsum += sm.f4[0][w]; fsq += sm.f4[1][w]; fmn = fminf(fmn, sm.f4[2][w]); fmx = fmaxf(fmx, sm.f4[3][w]);
+  }
+  float thr = -INFINITY;
+  if (P.do_topk && !raw) {
+    bool found = false;
+    const bool finite = isfinite(fmn) && isfinite(fmx) && isfinite(fsq);
+    const float inv_n = 1.0f / (float)cfg.ncols;
+    const float mean = fsum * inv_n;
+    const float sd = sqrtf(fmaxf(fsq * inv_n - mean * mean, 0.f));
+    if (finite && fmn == fmx) { thr = fmx; found = true; }
+    if (!found && finite) {
+      const float lo = mean + (z_run - win_run) * sd, hi = mean + (z_run + win_run) * sd;
+      if (lo < hi) found = bracket_select<NE, NT>(s, cfg.top_k, lo, hi, park, sm, &thr);
+    }
+    if (!found) {
+      __syncthreads();
+      float tmp[NE];
+#pragma unroll
+      for (int e = 0; e < NE; ++e) tmp[e] = s[e];
+      thr = select_slow<NE>(tmp, cfg.top_k, fmn, fmx, sm);
+      __syncthreads();
+    }
+    const float z_obs = (thr - mean) / sd;
+    if (isfinite(z_obs)) { z_run = z_obs; win_run = P.win_sd; }
+  }
+  const ExpShift ex(fmx);
+  float part = 0.f;
+#pragma unroll
+  for (int e = 0; e < NE; ++e) part += (s[e] >= thr) ? ex(s[e]) : 0.f;
+  part = warp_reduce(part, OpSum());
+  __syncthreads();
+  if (lane == 0) part_scr[warp] = part;
+  __syncthreads();
+  float tot = 0.f;
+#pragma unroll 8
+  for (int w = 0; w < NW; ++w) tot += part_scr[w];
+  const float inv = __fdiv_rn(1.0f, tot);
+#pragma unroll
+  for (int q = 0; q < NQ; ++q) {
+    const int e0 = (q * NT + tid) * 4;
+    float4 o;
+    o.x = s[q * 4 + 0] >= thr ? __fmul_rn(ex(s[q * 4 + 0]), inv) : 0.f;
+    o.y = s[q * 4 + 1] >= thr ? __fmul_rn(ex(s[q * 4 + 1]), inv) : 0.f;
+    o.z = s[q * 4 + 2] >= thr ? __fmul_rn(ex(s[q * 4 + 2]), inv) : 0.f;
+    o.w = s[q * 4 + 3] >= thr ? __fmul_rn(ex(s[q * 4 + 3]), inv) : 0.f;
+    *reinterpret_cast<float4*>(p + e0) = o;
+  }
+}
+
+template <int DT, bool VEC, int LNE>
 __global__ void __launch_bounds__(kWalkThreads) walk_kernel(const AcceptParams P) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const lantern_accept_cfg& cfg = P.cfg;
@@ -344,7 +428,11 @@ __global__ void __launch_bounds__(kWalkThreads) walk_kernel(const AcceptParams P
   S.sib = reinterpret_cast<int*>(smem_raw + o);             o += kMaxSib * 4;
   S.fscr = reinterpret_cast<float*>(smem_raw + o);          o += 36 * 4;
   S.iscr = reinterpret_cast<int*>(smem_raw + o);            o += 40 * 4;
-  S.pid = reinterpret_cast<int*>(smem_raw + o);
+  S.pid = reinterpret_cast<int*>(smem_raw + o);                 o += (size_t)(((D + 1) * L + 3) & ~3) * 4;
+  float* lazy_park = reinterpret_cast<float*>(smem_raw + o);   // [LNE][kWalkThreads] (lazy mode only)
+  __shared__ SelectSmem lazy_sm;
+  __shared__ float lazy_part[32];
+  float z_run = P.z_guess, win_run = P.win_sd_first;
 
   const int* ri_g = P.in.retrieve + (cfg.retrieve_shared ? 0 : (size_t)b * L * D);
   const int* tok_g = P.in.tree_tokens + (size_t)b * T;
@@ -400,7 +488,12 @@ __global__ void __launch_bounds__(kWalkThreads) walk_kernel(const AcceptParams P
   };
   auto set_distribution = [&](int node, bool raw) {
     const long long row = (long long)b * T + node;
-    RowStats st = P.stats[row];
+    RowStats st;
+    if (LNE > 0) {   // lazy mode: only the row class is needed up front
+      st.kind = P.in.row_kinds ? (int)P.in.row_kinds[row] : LANTERN_ROW_IMAGE;
+    } else {
+      st = P.stats[row];
+    }
     __syncthreads();
     extra_tok = -1; p_extra = 0.f; p_out = 0.f; scale = 1.0f;
     if (st.kind != LANTERN_ROW_IMAGE) {
@@ -412,6 +505,8 @@ __global__ void __launch_bounds__(kWalkThreads) walk_kernel(const AcceptParams P
         if (tid == 0) S.p[extra_tok - col0] = 1.0f;
         extra_tok = -1; p_extra = 0.f;
       }
+    } else if (LNE > 0) {
+      lazy_probs<DT, (LNE > 0 ? LNE : 4)>(P, b, node, raw, S.p, lazy_park, lazy_sm, lazy_part, z_run, win_run);
     } else {
       if (raw) st = raw_row_stats<DT, VEC>(P, b, node, S.fscr, S.dscr);
       load_probs<DT, VEC>(P, b, node, st, S.p, raw);
@@ -698,8 +793,8 @@ __global__ void __launch_bounds__(kWalkThreads) walk_kernel(const AcceptParams P
 // ----------------------------------------------------------------------------------------------
 // Host side
 // ----------------------------------------------------------------------------------------------
-static size_t walk_smem_bytes(const lantern_accept_cfg& c) {
-  size_t o = 0;
+static size_t walk_smem_bytes(const lantern_accept_cfg& c, int lazy_ne) {
+  size_t o = (size_t)lazy_ne * kWalkThreads * 4;
   o += (size_t)((c.ncols + 3) & ~3) * 4;
   o += (size_t)((((c.ncols + 31) >> 5) + 3) & ~3) * 4;
   o += 34 * 8;
@@ -709,7 +804,7 @@ static size_t walk_smem_bytes(const lantern_accept_cfg& c) {
   o += (size_t)kWalkThreads * 4;
   o += (size_t)((c.n_rows + 4) & ~3) * 4;
   o += kMaxSib * 4 + 36 * 4 + 40 * 4;
-  o += (size_t)(c.depth + 1) * c.n_paths * 4 + 16;
+  o += (size_t)((((c.depth + 1) * c.n_paths) + 3) & ~3) * 4 + 16;
   return o;
 }
 
@@ -773,7 +868,7 @@ static int launch_all(const AcceptParams& P, cudaStream_t stream, int phases) {
     else LAUNCH_FAST_MODE(NT, NQ, 2);           \
   } while (0)
 #define LAUNCH_STATS(NT, NQ) LAUNCH_STATS_MODE(NT, NQ, VEC, 0)
-  if (!(phases & 1)) {
+  if (!(phases & 1) || (phases & 4)) {
   } else if (mode) {
     if (nt == 256 && nq_inst == 2) LAUNCH_FAST(256, 2);
     else if (nt == 256 && nq_inst == 4) LAUNCH_FAST(256, 4);
@@ -803,20 +898,41 @@ static int launch_all(const AcceptParams& P, cudaStream_t stream, int phases) {
 #undef LAUNCH_STATS_MODE
 #undef LAUNCH_STATS
   LANTERN_CUDA(cudaGetLastError());
-  if ((phases & 1) && P.do_topp) {   // nucleus cut on top of the row statistics (slow path, one CTA per row)
+  if ((phases & 1) && !(phases & 4) && P.do_topp) {   // nucleus cut on top of the row statistics (slow path, one CTA per row)
     row_topp_kernel<DT, VEC><<<(unsigned)rows, kToppThreads, 0, stream>>>(P);
     LANTERN_CUDA(cudaGetLastError());
   }
   if (!(phases & 2)) return LANTERN_OK;
-  const size_t smem = walk_smem_bytes(c);
+  // lazy mode (phases bit 2): the walk computes the statistics of the rows it visits itself
+  int lazy_ne = 0;
+  if ((phases & 4) && VEC && !P.do_topp && c.ncols % (4 * kWalkThreads) == 0) {
+    const int ne = c.ncols / kWalkThreads;
+    if (ne == 4 || ne == 8 || ne == 16 || ne == 32) lazy_ne = ne;
+  }
+  if ((phases & 4) && !lazy_ne) {
+    set_error("lazy statistics need a vector-aligned window of 4096/8192/16384/32768 columns and no top-p");
+    return LANTERN_E_UNSUPPORTED;
+  }
+  const size_t smem = walk_smem_bytes(c, lazy_ne);
   if (smem > 227 * 1024) {
     set_error("walk kernel needs %zu bytes of shared memory (> 227 KB): ncols too large", smem);
     return LANTERN_E_UNSUPPORTED;
   }
-  auto kern = walk_kernel<DT, VEC>;
-  if (smem > 48 * 1024)
-    LANTERN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  kern<<<c.n_items, kWalkThreads, smem, stream>>>(P);
+#define LAUNCH_WALK(V, NE)                                                                          \
+  do {                                                                                              \
+    auto kern = walk_kernel<DT, V, NE>;                                                             \
+    if (smem > 48 * 1024)                                                                           \
+      LANTERN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    kern<<<c.n_items, kWalkThreads, smem, stream>>>(P);                                             \
+  } while (0)
+  switch (lazy_ne) {
+    case 0: LAUNCH_WALK(VEC, 0); break;
+    case 4: LAUNCH_WALK(true, 4); break;
+    case 8: LAUNCH_WALK(true, 8); break;
+    case 16: LAUNCH_WALK(true, 16); break;
+    default: LAUNCH_WALK(true, 32); break;
+  }
+#undef LAUNCH_WALK
   LANTERN_CUDA(cudaGetLastError());
   return LANTERN_OK;
 }

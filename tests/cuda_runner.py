@@ -33,7 +33,7 @@ def pad_retrieve(ri_list: Sequence[np.ndarray]) -> np.ndarray:
 
 
 def run_cases(cases: List[C.Built], dtype=torch.float32, want_sample_p: bool = True, device="cuda",
-              philox: Optional[tuple] = None):
+              philox: Optional[tuple] = None, phases: int = 3):
     """All cases must share family / knobs / T (they become one batched launch)."""
     b0 = cases[0]
     p = b0.params
@@ -75,7 +75,7 @@ def run_cases(cases: List[C.Built], dtype=torch.float32, want_sample_p: bool = T
     else:
         retrieve = torch.from_numpy(pad_retrieve([c.tree.retrieve_indices for c in cases])).to(dev)
     res = v.step(cond, uncond, tokens, retrieve, row_kinds=kinds, uniforms=uni,
-                 philox=philox or (0, 0), want_sample_p=want_sample_p, **kw)
+                 philox=philox or (0, 0), want_sample_p=want_sample_p, phases=phases, **kw)
     torch.cuda.synchronize()
     return res
 

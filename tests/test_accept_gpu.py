@@ -194,3 +194,27 @@ def test_top_p(top_p, top_k, temp):
     res = R.run_cases(built)
     for i, o in enumerate(orcs):
         R.compare(res, i, o)
+
+
+@pytest.mark.parametrize("family,kw", [
+    ("llamagen", dict()),
+    ("llamagen", dict(ncols=4096, top_k=500, lantern_k=10, lantern_delta=5.0, boost=11.0)),
+    ("anole", dict()),
+    ("lumina_mgpt", dict(depth=5, newline_depth=1)),
+    ("llamagen", dict(ncols=4096, static_tree="mc_sim_7b_63", lantern_k=10, lantern_delta=10.0, top_k=500, boost=8.5)),
+])
+def test_lazy_statistics_mode(family, kw):
+    """phases = 6: no streamed statistics kernel; the walk computes the statistics of the rows it visits."""
+    built, orcs, seed = [], [], 41000
+    while len(built) < 6:
+        b = C.build(dict(family=family, seed=seed, **kw))
+        seed += 1
+        o = C.oracle_step(b)
+        if o.margin >= MARGIN:
+            built.append(b)
+            orcs.append(o)
+    res = R.run_cases(built, phases=6)
+    for i, o in enumerate(orcs):
+        R.compare(res, i, o)
+    eager = R.run_cases(built, phases=3)
+    assert torch.equal(res.accept_length, eager.accept_length) and torch.equal(res.token, eager.token)

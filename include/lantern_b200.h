@@ -196,6 +196,22 @@ LANTERN_API int lantern_kv_compact(const lantern_kv_cfg* cfg, void* const* slab_
 LANTERN_API int lantern_build_neighbors(const float* E_dev, int32_t N, int32_t d, int32_t K, int32_t* out_dev,
                             void* stream);
 
+/*
+ * Dynamic (EAGLE-2) draft-tree post-processing: the host loops at the end of the drafter's topK_genrate
+ * (models/drafters/cnets_llamagen.py:831-908, cnets_lumina_mgpt.py:1330-1393).  Per prompt: scores [n_cand] =
+ * cat(scores_list), tokens [n_cand] = cat(ss_token), parents [n_groups] = cat(parents_list) (parent flat id + 1 of
+ * each group of `top_k` siblings, 0 = root).  Outputs: tree_tokens [B,T] (draft_tokens, root = sample token),
+ * parent [B,T], depth [B,T] (tree_position_ids), mask [B,T,T] (tree_mask, optional), retrieve [B,T,d_max]
+ * (retrieve_indices, -1 padded; valid block is counts[b] = {n_leaves, max_depth+1}); rows sorted like the reference
+ * does when a logits processor is present if sort_rows != 0.  top-k tie rule: higher score, then lower flat index.
+ */
+LANTERN_API int lantern_build_dynamic_tree(const float* scores_dev, const int32_t* tokens_dev, const int32_t* parents_dev,
+                                           const int32_t* root_tokens_dev, int32_t n_items, int32_t n_cand,
+                                           int32_t n_groups, int32_t top_k, int32_t total_tokens, int32_t d_max,
+                                           int32_t sort_rows, int32_t* tree_tokens_dev, int32_t* parent_dev,
+                                           int32_t* depth_dev, float* mask_dev, int32_t* retrieve_dev,
+                                           int32_t* counts_dev, void* stream);
+
 /* Test hook of the tensor-core path of lantern_build_neighbors: the approximate squared-distance matrix
  * D~[i][j] = |e_i|^2 + |e_j|^2 - 2 e_i.e_j (tcgen05, TF32 cross term), fp32 [N, ld], diagonal = +inf. */
 LANTERN_API int lantern_debug_dist_gemm(const float* E_dev, int32_t N, int32_t d, float* D_dev, int32_t ld, void* stream);

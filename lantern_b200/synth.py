@@ -274,3 +274,58 @@ def static_group_counts(tree_choices) -> List[int]:
     for lvl in range(1, maxd):
         counts.append(len({p[:-1] for p in nodes if len(p) == lvl + 1}))
     return counts
+
+
+# --------------------------------------------------------------------------- #
+# Drafter expansion outputs (inputs of the dynamic-tree post-processing)
+# --------------------------------------------------------------------------- #
+@dataclass
+class Expansion:
+    scores: np.ndarray     # [n_cand] fp32  cat(scores_list)           (cnets_llamagen.py:831)
+    tokens: np.ndarray     # [n_cand] int64 cat(ss_token)              (:832)
+    parents: np.ndarray    # [1 + depth * top_k] int64 cat(parents_list) (:840)
+    sample_token: int
+    top_k: int
+    depth: int
+
+
+def eagle2_expansion(seed: int, depth: int = 4, top_k: int = 10, lo: int = 0, hi: int = 16384) -> Expansion:
+    """What the drafter's expansion loop (cnets_llamagen.py:766-821) leaves behind: per level the top_k children of
+    each of the top_k frontier nodes with cumulative log-prob scores, the frontier chosen by cumulative score, and
+    the `parents` bookkeeping (parent flat id + 1 per sibling group, bias rule of :788-791)."""
+    rng = hash_u64(seed, 4 * top_k * top_k * (depth + 2), stream=61)
+    cursor = [0]
+
+    def logprobs(n_par):
+        k = n_par * top_k
+        u = ((rng[cursor[0]:cursor[0] + k] >> np.uint64(40)).astype(np.float64) + 0.5) / 16777216.0
+        cursor[0] += k
+        lp = np.log(u).reshape(n_par, top_k) * 0.8 - 0.05
+        return -np.sort(-lp, axis=1).astype(np.float32)        # descending like topk(log_softmax)
+
+    def toks(n_par):
+        k = n_par * top_k
+        t = lo + (rng[cursor[0]:cursor[0] + k] % np.uint64(hi - lo)).astype(np.int64)
+        cursor[0] += k
+        return t.reshape(n_par, top_k)
+
+    scores_list = [logprobs(1)]
+    tokens_list = [toks(1)]
+    parents_list = [np.zeros(1, dtype=np.int64)]
+    scores = scores_list[0][0].copy()
+    topk_cs_index = np.arange(top_k)
+    for i in range(depth):
+        bias1 = top_k if i > 0 else 0
+        bias2 = max(0, i - 1)
+        bias = 1 + top_k ** 2 * bias2 + bias1
+        parents_list.append((topk_cs_index + bias).astype(np.int64))
+        cu = (logprobs(top_k) + scores[:, None]).astype(np.float32)
+        tokens_list.append(toks(top_k))
+        order = np.argsort(-cu.reshape(-1), kind="stable")[:top_k]
+        topk_cs_index = order
+        scores = cu.reshape(-1)[order]
+        scores_list.append(cu)
+    return Expansion(np.concatenate([s.reshape(-1) for s in scores_list]).astype(np.float32),
+                     np.concatenate([t.reshape(-1) for t in tokens_list]).astype(np.int64),
+                     np.concatenate(parents_list).astype(np.int64),
+                     lo + int(rng[-1] % np.uint64(hi - lo)), top_k, depth)

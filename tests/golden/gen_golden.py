@@ -236,9 +236,45 @@ def tree_buffer_fixtures(R):
     return out
 
 
+def dynamic_tree_fixtures():
+    """Execute the reference's own dynamic-tree post-processing (the tail of Model.topK_genrate,
+    models/drafters/cnets_llamagen.py:831-912) on synthetic expansion outputs.  The code is taken from the mounted
+    reference at generation time (inspect.getsource) and never written to this repository."""
+    import inspect
+    import textwrap
+    from lantern_b200 import synth
+    cn = importlib.import_module("models.drafters.cnets_llamagen")
+    src = inspect.getsource(cn.Model.topK_genrate)
+    start = src.index("scores_list = torch.cat(scores_list, dim=0).view(-1)")
+    end = src.index("return draft_tokens, retrieve_indices, tree_mask, tree_position_ids")
+    body = textwrap.dedent(" " * 8 + src[start:end])
+    out = []
+    for seed, depth, total in [(1, 4, 58), (2, 4, 58), (3, 5, 58), (4, 5, 58), (5, 4, 25), (6, 3, 99), (7, 6, 120),
+                               (8, 4, 9), (9, 5, 58), (10, 4, 58)]:
+        ex = synth.eagle2_expansion(seed, depth=depth, top_k=10)
+        for sort_rows in (True, False):
+            k = ex.top_k
+            sizes = [k] + [k * k] * depth
+            sl = [t.view(-1, k) for t in torch.split(torch.from_numpy(ex.scores), sizes)]
+            tl = [t.view(-1, k) for t in torch.split(torch.from_numpy(ex.tokens), sizes)]
+            pl = list(torch.split(torch.from_numpy(ex.parents), [1] + [k] * depth))
+            ns = {"torch": torch, "scores_list": sl, "ss_token": tl, "parents_list": pl, "total_tokens": total,
+                  "top_k": k, "sample_token": torch.tensor([ex.sample_token]),
+                  "logits_processor": (object() if sort_rows else None), "hidden_states": torch.zeros(1)}
+            exec(body, ns)
+            out.append({"seed": seed, "depth": depth, "total_tokens": total, "sort_rows": sort_rows,
+                        "draft_tokens": ns["draft_tokens"][0].tolist(),
+                        "retrieve_indices": ns["retrieve_indices"].tolist(),
+                        "tree_position_ids": ns["tree_position_ids"].tolist(),
+                        "tree_mask": ns["tree_mask"][0, 0].to(torch.int64).tolist()})
+    return out
+
+
 def main():
     torch.set_num_threads(max(1, os.cpu_count() or 1))
     R = import_reference()
+    with open(os.path.join(HERE, "dynamic_trees.json"), "w") as f:
+        json.dump(dynamic_tree_fixtures(), f)
     kept, dropped, mismatched, worst_sp = [], 0, 0, 0.0
     for p in case_list():
         b = C.build(p)

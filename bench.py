@@ -210,7 +210,7 @@ def run_reference(args):
         "impl": "reference", "metric": "images/sec (verification hot path)", "value": value, "unit": "images/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_all / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args, n_items),
+        "config": dict(workload_config(args, n_items), launch="host processes, one per core"),
         "cpu_baseline": {"value": value, "unit": "images/s", "cores": cores, "kind": "port",
                          "sample": f"{n_items} prompts x {args.steps} verify steps, oracle/lantern_oracle.py eager "
                                    f"(all T rows post-processed + [L,D,V] gather, as the reference does), one process per core"},

@@ -212,6 +212,18 @@ LANTERN_API int lantern_build_dynamic_tree(const float* scores_dev, const int32_
                                            int32_t* depth_dev, float* mask_dev, int32_t* retrieve_dev,
                                            int32_t* counts_dev, void* stream);
 
+/*
+ * Static-tree drafter sampling (Model.sample, models/drafters/cnets_llamagen.py:924-940): for each of the
+ * n_items * n_rows logits rows (cond / optional uncond, warped with cfg's temperature / top_p / top_k) write the
+ * full distribution probs [rows, V] (`op`), k tokens drawn without replacement idx [rows, k] (exponential race on
+ * the device Philox stream cfg.philox_seed / philox_step; same law as torch.multinomial(p, k, False)) and their
+ * conditional probabilities p_i / (1 - sum_{j<i} p_j) clamped to [0,1] (cond_probs [rows, k]).
+ * Only the shape / window / dtype / warp / philox fields of cfg and in->logits_* are used.
+ */
+LANTERN_API int lantern_draft_sample(const lantern_accept_cfg* cfg, const lantern_accept_in* in, int32_t k,
+                                     float* probs_dev, int32_t* idx_dev, float* cond_probs_dev, void* workspace_dev,
+                                     size_t workspace_bytes, void* stream);
+
 /* Test hook of the tensor-core path of lantern_build_neighbors: the approximate squared-distance matrix
  * D~[i][j] = |e_i|^2 + |e_j|^2 - 2 e_i.e_j (tcgen05, TF32 cross term), fp32 [N, ld], diagonal = +inf. */
 LANTERN_API int lantern_debug_dist_gemm(const float* E_dev, int32_t N, int32_t d, float* D_dev, int32_t ld, void* stream);

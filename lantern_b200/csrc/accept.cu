@@ -18,6 +18,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 
 #include "common.cuh"
 #include "accept_types.cuh"
@@ -998,6 +999,59 @@ static int validate(const lantern_accept_cfg& c, const lantern_accept_in& in, co
   return LANTERN_OK;
 }
 
+static void fill_params(AcceptParams& P, const lantern_accept_cfg* cfg, const lantern_accept_in* in,
+                        const lantern_accept_out* out, void* workspace_dev) {
+  P.cfg = *cfg;
+  P.in = *in;
+  if (out) P.out = *out; else memset(&P.out, 0, sizeof(P.out));
+  P.stats = static_cast<RowStats*>(workspace_dev);
+  P.mix.cfg_scale = cfg->cfg_scale;
+  P.mix.temperature = cfg->temperature;
+  P.mix.has_uncond = in->logits_uncond != nullptr;
+  P.mix.do_temp = cfg->temperature != 1.0f;
+  P.do_topk = cfg->top_k > 0 && cfg->top_k < cfg->ncols;
+  P.do_topp = (1e-8f <= cfg->top_p && cfg->top_p < 1.0f) ? 1 : 0;
+  P.z_guess = P.do_topk ? (float)norm_ppf(1.0 - (double)cfg->top_k / (double)cfg->ncols) : 0.f;
+  P.win_sd = 0.08f;
+  P.win_sd_first = 0.25f;
+  if (const char* w = getenv("LANTERN_WIN_SD")) P.win_sd = (float)atof(w);   // tuning knob (any value keeps the select exact)
+  P.tail_raw = cfg->family == LANTERN_FAMILY_VANILLA;
+  P.lumina = cfg->family == LANTERN_FAMILY_LUMINA;
+  P.static_zero_q = cfg->static_tree && cfg->family != LANTERN_FAMILY_LUMINA;
+  const int eb = cfg->logits_dtype == LANTERN_F32 ? 4 : 2;
+  const uintptr_t align = eb == 4 ? 16 : 8;
+  auto aligned = [&](const void* p) { return p == nullptr || (reinterpret_cast<uintptr_t>(p) % align) == 0; };
+  P.vec_ok = (cfg->col0 % 4 == 0) && (cfg->ncols % 4 == 0) && (cfg->row_stride % 4 == 0) &&
+             (cfg->item_stride % 4 == 0) && aligned(in->logits_cond) && aligned(in->logits_uncond);
+}
+
+static int dispatch_launch(const AcceptParams& P, cudaStream_t s, int phases) {
+#define DISPATCH(DT) return P.vec_ok ? launch_all<DT, true>(P, s, phases) : launch_all<DT, false>(P, s, phases)
+  switch (P.cfg.logits_dtype) {
+    case LANTERN_F32: DISPATCH(LANTERN_F32);
+    case LANTERN_BF16: DISPATCH(LANTERN_BF16);
+    default: DISPATCH(LANTERN_F16);
+  }
+#undef DISPATCH
+}
+
+// Row statistics alone (CFG mix, warpers) for callers that consume RowStats themselves (draft_sample.cu).
+int accept_row_stats_only(const lantern_accept_cfg* cfg, const lantern_accept_in* in, void* workspace_dev,
+                          size_t workspace_bytes, void* stream, AcceptParams* params_out) {
+  if (cfg->n_items <= 0 || cfg->n_rows <= 0 || cfg->vocab <= 0 || cfg->ncols <= 0 || cfg->col0 < 0 ||
+      cfg->col0 + cfg->ncols > cfg->vocab || cfg->row_stride < cfg->ncols || !in->logits_cond ||
+      cfg->logits_dtype < LANTERN_F32 || cfg->logits_dtype > LANTERN_F16 || !(cfg->temperature > 1e-5f)) {
+    set_error("row statistics: bad shape / window / dtype / temperature");
+    return LANTERN_E_INVALID;
+  }
+  if (!workspace_dev || workspace_bytes < lantern_accept_workspace_bytes(cfg)) {
+    set_error("row statistics: workspace too small");
+    return LANTERN_E_WORKSPACE;
+  }
+  fill_params(*params_out, cfg, in, nullptr, workspace_dev);
+  return dispatch_launch(*params_out, static_cast<cudaStream_t>(stream), 1);
+}
+
 extern "C" int lantern_accept_fused(const lantern_accept_cfg* cfg, const lantern_accept_in* in,
                                     const lantern_accept_out* out, void* workspace_dev, size_t workspace_bytes,
                                     void* stream) {
@@ -1019,35 +1073,6 @@ extern "C" int lantern_accept_phases(const lantern_accept_cfg* cfg, const lanter
     return LANTERN_E_WORKSPACE;
   }
   AcceptParams P;
-  P.cfg = *cfg;
-  P.in = *in;
-  P.out = *out;
-  P.stats = static_cast<RowStats*>(workspace_dev);
-  P.mix.cfg_scale = cfg->cfg_scale;
-  P.mix.temperature = cfg->temperature;
-  P.mix.has_uncond = in->logits_uncond != nullptr;
-  P.mix.do_temp = cfg->temperature != 1.0f;
-  P.do_topk = cfg->top_k > 0 && cfg->top_k < cfg->ncols;
-  P.do_topp = (1e-8f <= cfg->top_p && cfg->top_p < 1.0f) ? 1 : 0;
-  P.z_guess = P.do_topk ? (float)norm_ppf(1.0 - (double)cfg->top_k / (double)cfg->ncols) : 0.f;
-  P.win_sd = 0.08f;
-  P.win_sd_first = 0.25f;
-  if (const char* w = getenv("LANTERN_WIN_SD")) P.win_sd = (float)atof(w);   // tuning knob (any value keeps the select exact)
-  P.tail_raw = cfg->family == LANTERN_FAMILY_VANILLA;
-  P.lumina = cfg->family == LANTERN_FAMILY_LUMINA;
-  P.static_zero_q = cfg->static_tree && cfg->family != LANTERN_FAMILY_LUMINA;
-  const int eb = cfg->logits_dtype == LANTERN_F32 ? 4 : 2;
-  const uintptr_t align = eb == 4 ? 16 : 8;
-  auto aligned = [&](const void* p) { return p == nullptr || (reinterpret_cast<uintptr_t>(p) % align) == 0; };
-  P.vec_ok = (cfg->col0 % 4 == 0) && (cfg->ncols % 4 == 0) && (cfg->row_stride % 4 == 0) &&
-             (cfg->item_stride % 4 == 0) && aligned(in->logits_cond) && aligned(in->logits_uncond);
-  cudaStream_t s = static_cast<cudaStream_t>(stream);
-#define DISPATCH(DT)                                        \
-  return P.vec_ok ? launch_all<DT, true>(P, s, phases) : launch_all<DT, false>(P, s, phases)
-  switch (cfg->logits_dtype) {
-    case LANTERN_F32: DISPATCH(LANTERN_F32);
-    case LANTERN_BF16: DISPATCH(LANTERN_BF16);
-    default: DISPATCH(LANTERN_F16);
-  }
-#undef DISPATCH
+  fill_params(P, cfg, in, out, workspace_dev);
+  return dispatch_launch(P, static_cast<cudaStream_t>(stream), phases);
 }

@@ -151,3 +151,41 @@ def test_tensor_core_neighbor_table_bit_exact(N, d, K):
     finally:
         del os_env["LANTERN_NBR_EXACT_ONLY"]
     assert np.array_equal(exact, want)
+
+
+@pytest.mark.parametrize("top_k,temp,cfg", [(0, 1.0, False), (200, 1.0, True), (500, 0.8, True)])
+def test_draft_sample_matches_oracle(top_k, temp, cfg):
+    """Static-tree drafter sampling (next-row N3): tokens bit-exact, conditional probabilities and `op` within 1e-5."""
+    from lantern_b200 import draft_sample, posterior, synth
+    R_, V = 5, 4096
+    cond = synth.gauss(77, (R_, V), stream=1)
+    uncond = cond + synth.gauss(77, (R_, V), stream=2) * np.float32(0.25) if cfg else None
+    proc = posterior.prepare_logits_processor(temperature=temp, top_p=1.0, top_k=top_k)
+    idx, cp, probs = draft_sample.sample(torch.from_numpy(cond).cuda(), proc, k=10,
+                                         uncond=torch.from_numpy(uncond).cuda() if cfg else None, cfg_scale=3.0,
+                                         seed=99, step=4)
+    torch.cuda.synchronize()
+    for r in range(R_):
+        row = O.cfg_mix(cond[r], uncond[r], 3.0) if cfg else cond[r]
+        oi, ocp, op = O.draft_sample(row, O.Warp(temp, 1.0, top_k), 10, 99, 4, r)
+        assert idx[r].tolist() == oi.tolist()
+        R.assert_probs_close(probs[r].cpu().numpy(), op)
+        assert np.allclose(cp[r].cpu().numpy(), ocp, rtol=1e-5, atol=1e-7)
+        assert len(set(oi.tolist())) == 10                       # without replacement
+
+
+def test_draft_sample_law():
+    """The exponential race draws the first token with probability p (chi-square-free sanity check on a tiny vocab)."""
+    from lantern_b200 import draft_sample, posterior
+    V = 8
+    logits = torch.tensor([[2.0, 1.0, 0.0, -1.0, 0.5, 1.5, -0.5, 0.2]], device="cuda").repeat(1, 1)
+    p = torch.softmax(logits[0], 0).cpu().numpy()
+    proc = posterior.prepare_logits_processor(temperature=1.0, top_p=1.0, top_k=0)
+    counts = np.zeros(V)
+    n = 4000
+    big = logits.repeat(n, 1).contiguous()
+    idx, _, _ = draft_sample.sample(big, proc, k=3, seed=7, step=1)
+    first = idx[:, 0].cpu().numpy()
+    for t in first:
+        counts[t] += 1
+    assert np.abs(counts / n - p).max() < 0.03

@@ -218,3 +218,36 @@ def test_lazy_statistics_mode(family, kw):
         R.compare(res, i, o)
     eager = R.run_cases(built, phases=3)
     assert torch.equal(res.accept_length, eager.accept_length) and torch.equal(res.token, eager.token)
+
+
+def test_vanilla_llm_vocab_32000():
+    """Plain EAGLE verification on an LLM-sized vocabulary (non power of two -> generic statistics kernel)."""
+    built, orcs, seed = [], [], 52000
+    while len(built) < 3:
+        b = C.build(dict(family="vanilla", ncols=32000, cfg=False, lantern=False, top_k=50, boost=12.0, seed=seed))
+        seed += 1
+        o = C.oracle_step(b)
+        if o.margin >= MARGIN:
+            built.append(b)
+            orcs.append(o)
+    res = R.run_cases(built)
+    for i, o in enumerate(orcs):
+        R.compare(res, i, o)
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16])
+def test_lumina_bf16_window_misaligned_for_16_bytes(dtype):
+    """bf16 logits with the image window starting at column 4: 8-byte aligned only (TMA copies start 8 bytes early)."""
+    built, orcs, seed = [], [], 53000
+    while len(built) < 4:
+        b = C.build(dict(family="lumina_mgpt", depth=5, seed=seed))
+        seed += 1
+        b.cond = torch.from_numpy(b.cond).to(dtype).float().numpy()
+        b.uncond = torch.from_numpy(b.uncond).to(dtype).float().numpy()
+        o = C.oracle_step(b)
+        if o.margin >= MARGIN:
+            built.append(b)
+            orcs.append(o)
+    res = R.run_cases(built, dtype=dtype)
+    for i, o in enumerate(orcs):
+        R.compare(res, i, o)

@@ -50,9 +50,10 @@ def build(force: bool = False, verbose: bool = False) -> str:
     objdir = os.path.join(PKG, "build")
     os.makedirs(objdir, exist_ok=True)
     procs = []
+    extra = os.environ.get("LANTERN_EXTRA_NVCC_FLAGS", "").split()
     for src in SOURCES:
         obj = os.path.join(objdir, src.replace(".cu", ".o"))
-        cmd = [nvcc] + NVCC_FLAGS + ["-I", os.path.join(ROOT, "include"), "-c", os.path.join(CSRC, src), "-o", obj]
+        cmd = [nvcc] + NVCC_FLAGS + extra + ["-I", os.path.join(ROOT, "include"), "-c", os.path.join(CSRC, src), "-o", obj]
         procs.append((src, cmd, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
         objs.append(obj)
     for src, cmd, p in procs:

@@ -225,7 +225,8 @@ LANTERN_API int lantern_draft_sample(const lantern_accept_cfg* cfg, const lanter
                                      size_t workspace_bytes, void* stream);
 
 /* Test hook of the tensor-core path of lantern_build_neighbors: the approximate squared-distance matrix
- * D~[i][j] = |e_i|^2 + |e_j|^2 - 2 e_i.e_j (tcgen05, TF32 cross term), fp32 [N, ld], diagonal = +inf. */
+ * D~[i][j] = |e_i|^2 + |e_j|^2 - 2 e_i.e_j (tcgen05, TF32 cross term), fp32 [N, ld]. The diagonal holds
+ * the computed value (~0); the select stage excludes self by index. */
 LANTERN_API int lantern_debug_dist_gemm(const float* E_dev, int32_t N, int32_t d, float* D_dev, int32_t ld, void* stream);
 
 /* Which route the last lantern_build_neighbors call on this thread took: 1 = tensor-core candidates + exact

@@ -19,7 +19,9 @@
 
 namespace lantern {
 
-constexpr int kGemmThreads = 128;
+constexpr int kGemmThreads = 320;   // 8 epilogue warps + TMA producer warp + MMA issuer warp
+constexpr int kMaxStages = 6;
+constexpr int kGemmMaxDim = 256;   // the resident A block needs dpad * 512 bytes of shared memory
 constexpr int kTileM = 128, kTileN = 256, kChunkK = 32;   // K is consumed in chunks of 32 (4 MMAs of K = 8)
 constexpr int kSelThreads = 512;
 constexpr int kSelNE = 32;         // register-resident row: N <= 16384
@@ -55,128 +57,221 @@ __global__ void row_norms_kernel(const float* __restrict__ E, int N, int d, floa
   norms[i] = s;
 }
 
-__global__ void __launch_bounds__(kGemmThreads) dist_gemm_kernel(const float* __restrict__ E,
-                                                                 const float* __restrict__ norms, int N, int d,
-                                                                 float* __restrict__ Dout, int ld) {
+// Packs the codebook into the tensor-core operand layout once: TF32-rounded, zero-padded to [dpad/4][Npad][4], i.e.
+// for every 16-byte K chunk the rows are contiguous.  A 128- or 256-row operand tile of one K chunk is then one
+// contiguous 2 / 4 KiB run that a single cp.async.bulk moves straight into the canonical K-major SWIZZLE_NONE
+// shared-memory layout (core matrix = 8 rows x 16 bytes, SBO = 128 B, LBO = rows * 16 B).
+__global__ void pack_tf32_kernel(const float* __restrict__ E, int N, int d, int Npad, int dpad,
+                                 uint32_t* __restrict__ Epk) {
+  const int n4 = dpad / 4;
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < (size_t)Npad * n4;
+       idx += (size_t)gridDim.x * blockDim.x) {
+    const int c4 = (int)(idx % n4), row = (int)(idx / n4);
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (row < N) {
+      const float* src = E + (size_t)row * d;
+      const int k0 = c4 * 4;
+      if (k0 + 0 < d) v.x = to_tf32(src[k0 + 0]);
+      if (k0 + 1 < d) v.y = to_tf32(src[k0 + 1]);
+      if (k0 + 2 < d) v.z = to_tf32(src[k0 + 2]);
+      if (k0 + 3 < d) v.w = to_tf32(src[k0 + 3]);
+    }
+    *reinterpret_cast<uint4*>(Epk + ((size_t)c4 * Npad + row) * 4) = v;
+  }
+}
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// One thread's 32 accumulator columns [cb, cb+32) of its row: D~ = |a|^2 + |b|^2 - 2 a.b, stored as full 32-byte sectors.
+__device__ __forceinline__ void epilogue_block(const uint32_t (&r)[32], float na, const float* __restrict__ nbh,
+                                               float* __restrict__ drow, int cb, int colbase, int ld, bool row_ok,
+                                               bool wide) {
+  if (!row_ok) return;
+#pragma unroll
+  for (int j = 0; j < 32; j += 8) {
+    const float4 n0 = *reinterpret_cast<const float4*>(nbh + cb + j);
+    const float4 n1 = *reinterpret_cast<const float4*>(nbh + cb + j + 4);
+    float o[8];
+    o[0] = fmaf(-2.0f, __uint_as_float(r[j + 0]), na + n0.x);
+    o[1] = fmaf(-2.0f, __uint_as_float(r[j + 1]), na + n0.y);
+    o[2] = fmaf(-2.0f, __uint_as_float(r[j + 2]), na + n0.z);
+    o[3] = fmaf(-2.0f, __uint_as_float(r[j + 3]), na + n0.w);
+    o[4] = fmaf(-2.0f, __uint_as_float(r[j + 4]), na + n1.x);
+    o[5] = fmaf(-2.0f, __uint_as_float(r[j + 5]), na + n1.y);
+    o[6] = fmaf(-2.0f, __uint_as_float(r[j + 6]), na + n1.z);
+    o[7] = fmaf(-2.0f, __uint_as_float(r[j + 7]), na + n1.w);
+    const int c = colbase + cb + j;
+    if (wide) {   // one full 32-byte sector per thread (256-bit store, sm_100)
+      if (c + 7 < ld)
+        asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(drow + cb + j), "f"(o[0]),
+                     "f"(o[1]), "f"(o[2]), "f"(o[3]), "f"(o[4]), "f"(o[5]), "f"(o[6]), "f"(o[7])
+                     : "memory");
+    } else {
+      if (c + 3 < ld) *reinterpret_cast<float4*>(drow + cb + j) = make_float4(o[0], o[1], o[2], o[3]);
+      if (c + 7 < ld) *reinterpret_cast<float4*>(drow + cb + j + 4) = make_float4(o[4], o[5], o[6], o[7]);
+    }
+  }
+}
+
+// Warp-specialised persistent distance GEMM.  Grid (row blocks of 128, column-tile groups); per CTA:
+//   warp 8 (one lane)  TMA producer: the resident A block once, then B chunks through a kStages-deep ring
+//   warp 9 (one lane)  tcgen05.mma issuer: 4 MMAs (K = 8 each) per chunk into one of two 256-column TMEM accumulators
+//   warps 0-7          epilogue: tcgen05.ld of the other accumulator, + |a|^2 + |b|^2, fp32 stores (the diagonal
+//                      is left as computed, ~0; consumers exclude self by index)
+// so loads, tensor-core math and the store of the previous tile overlap.
+__global__ void __launch_bounds__(kGemmThreads) dist_gemm_kernel(const uint32_t* __restrict__ Epk,
+                                                                 const float* __restrict__ norms, int N, int Npad,
+                                                                 int dpad, int n_stages, float* __restrict__ Dout,
+                                                                 int ld) {
   extern __shared__ __align__(128) unsigned char smem[];
-  uint32_t* sA = reinterpret_cast<uint32_t*>(smem);                                  // [kChunkK/4][kTileM][4]
-  uint32_t* sB = reinterpret_cast<uint32_t*>(smem + kChunkK * kTileM * 4);           // [kChunkK/4][kTileN][4]
-  float* sNb = reinterpret_cast<float*>(smem + kChunkK * (kTileM + kTileN) * 4);     // [kTileN]
-  __shared__ __align__(8) uint64_t mbar;
+  const int n_chunks = dpad / kChunkK;
+  constexpr uint32_t kStageBytes = kChunkK * kTileN * 4;
+  uint32_t* sA = reinterpret_cast<uint32_t*>(smem);                                 // [dpad/4][kTileM][4]
+  unsigned char* sB = smem + (size_t)dpad * kTileM * 4;                             // [n_stages][kChunkK/4][kTileN][4]
+  float* sNb = reinterpret_cast<float*>(sB + (size_t)n_stages * kStageBytes);       // [2][kTileN]
+  __shared__ __align__(8) uint64_t bar_a, bar_full[kMaxStages], bar_empty[kMaxStages], bar_tfull[2], bar_tempty[2];
   __shared__ uint32_t tmem_base_smem;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int row0 = blockIdx.x * kTileM;
-  const int dpad = (d + kChunkK - 1) / kChunkK * kChunkK;
   const int n_col_tiles = (N + kTileN - 1) / kTileN;
 
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_smem)),
-                 "n"(kTileN));
+                 "n"(2 * kTileN));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
-  if (tid == 0) mbar_init(&mbar, 1);
+  if (tid == 0) {
+    mbar_init(&bar_a, 1);
+    for (int i = 0; i < n_stages; ++i) { mbar_init(&bar_full[i], 1); mbar_init(&bar_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&bar_tfull[i], 1); mbar_init(&bar_tempty[i], 8); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
   asm volatile("tcgen05.fence::before_thread_sync;");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;");
   const uint32_t tmem_base = tmem_base_smem;
-  const uint32_t idesc = make_instr_desc(kTileM, kTileN);
-  uint32_t parity = 0;
-  const int my_row = row0 + tid;   // accumulator lane == thread
-  const float na = my_row < N ? norms[my_row] : 0.f;
 
-  for (int ct = blockIdx.y; ct < n_col_tiles; ct += gridDim.y) {
-    const int col0 = ct * kTileN;
-    for (int j = tid; j < kTileN; j += kGemmThreads) sNb[j] = (col0 + j < N) ? norms[col0 + j] : 0.f;
-    for (int kc0 = 0; kc0 < dpad; kc0 += kChunkK) {
-      // ---- stage the operand chunks: [K chunk of 4][row][4 tf32] ----
-      for (int idx = tid; idx < kTileM * (kChunkK / 4); idx += kGemmThreads) {
-        const int r = idx % kTileM, c4 = idx / kTileM;
-        uint4 v = make_uint4(0, 0, 0, 0);
-        const int gr = row0 + r, k0 = kc0 + c4 * 4;
-        if (gr < N) {
-          const float* src = E + (size_t)gr * d + k0;
-          v.x = k0 + 0 < d ? to_tf32(src[0]) : 0u;
-          v.y = k0 + 1 < d ? to_tf32(src[1]) : 0u;
-          v.z = k0 + 2 < d ? to_tf32(src[2]) : 0u;
-          v.w = k0 + 3 < d ? to_tf32(src[3]) : 0u;
+  if (warp == 8) {
+    if (lane == 0) {
+      mbar_expect_tx(&bar_a, (uint32_t)dpad * kTileM * 4);
+      for (int c4 = 0; c4 < dpad / 4; ++c4)
+        bulk_g2s(sA + (size_t)c4 * kTileM * 4, Epk + ((size_t)c4 * Npad + row0) * 4, kTileM * 16, &bar_a);
+      int it = 0;
+      for (int ct = blockIdx.y; ct < n_col_tiles; ct += gridDim.y) {
+        const int col0 = ct * kTileN;
+        for (int c = 0; c < n_chunks; ++c, ++it) {
+          const int st = it % n_stages;
+          const uint32_t ph = (uint32_t)(it / n_stages) & 1u;
+          mbar_wait(&bar_empty[st], ph ^ 1u);   // first pass over the ring falls through
+          mbar_expect_tx(&bar_full[st], kStageBytes);
+          unsigned char* dst = sB + (size_t)st * kStageBytes;
+#pragma unroll
+          for (int q = 0; q < kChunkK / 4; ++q)
+            bulk_g2s(dst + (size_t)q * kTileN * 16, Epk + ((size_t)(c * (kChunkK / 4) + q) * Npad + col0) * 4,
+                     kTileN * 16, &bar_full[st]);
         }
-        *reinterpret_cast<uint4*>(sA + ((size_t)c4 * kTileM + r) * 4) = v;
       }
-      for (int idx = tid; idx < kTileN * (kChunkK / 4); idx += kGemmThreads) {
-        const int r = idx % kTileN, c4 = idx / kTileN;
-        uint4 v = make_uint4(0, 0, 0, 0);
-        const int gr = col0 + r, k0 = kc0 + c4 * 4;
-        if (gr < N) {
-          const float* src = E + (size_t)gr * d + k0;
-          v.x = k0 + 0 < d ? to_tf32(src[0]) : 0u;
-          v.y = k0 + 1 < d ? to_tf32(src[1]) : 0u;
-          v.z = k0 + 2 < d ? to_tf32(src[2]) : 0u;
-          v.w = k0 + 3 < d ? to_tf32(src[3]) : 0u;
-        }
-        *reinterpret_cast<uint4*>(sB + ((size_t)c4 * kTileN + r) * 4) = v;
-      }
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> async-proxy (MMA) reads
-      __syncthreads();
-      if (tid == 0) {
+    }
+  } else if (warp == 9) {
+    if (lane == 0) {
+      const uint32_t idesc = make_instr_desc(kTileM, kTileN);
+      mbar_wait(&bar_a, 0);
+      int it = 0, t = 0;
+      for (int ct = blockIdx.y; ct < n_col_tiles; ct += gridDim.y, ++t) {
+        const int b = t & 1;
+        mbar_wait(&bar_tempty[b], ((uint32_t)(t >> 1) & 1u) ^ 1u);   // the epilogue drained this accumulator
         asm volatile("tcgen05.fence::after_thread_sync;");
+        const uint32_t d_tmem = tmem_base + (uint32_t)(b * kTileN);
+        for (int c = 0; c < n_chunks; ++c, ++it) {
+          const int st = it % n_stages;
+          mbar_wait(&bar_full[st], (uint32_t)(it / n_stages) & 1u);
+          asm volatile("tcgen05.fence::after_thread_sync;");
+          const uint32_t b_addr = smem_u32(sB + (size_t)st * kStageBytes);
 #pragma unroll
-        for (int s = 0; s < kChunkK / 8; ++s) {
-          const uint64_t adesc = make_smem_desc(smem_u32(sA) + s * 2 * (kTileM * 16), kTileM * 16, 128);
-          const uint64_t bdesc = make_smem_desc(smem_u32(sB) + s * 2 * (kTileN * 16), kTileN * 16, 128);
-          const uint32_t accumulate = (kc0 > 0 || s > 0) ? 1u : 0u;
-          asm volatile(
-              "{\n"
-              ".reg .pred p;\n"
-              "setp.ne.b32 p, %4, 0;\n"
-              "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
-              "}\n" ::"r"(tmem_base),
-              "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate));
-        }
-        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.b64 [%0];" ::"r"(smem_u32(&mbar)) : "memory");
-      }
-      mbar_wait(&mbar, parity);   // the MMAs of this chunk are done: operands may be overwritten
-      parity ^= 1;
-      asm volatile("tcgen05.fence::after_thread_sync;");
-    }
-    // ---- epilogue: TMEM -> registers, add the norms, store the tile row by row ----
-    const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16);
-#pragma unroll 1
-    for (int cb = 0; cb < kTileN; cb += 32) {
-      uint32_t r[32];
-      asm volatile(
-          "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-          "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-          "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-          : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-            "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
-            "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
-            "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-          : "r"(lane_addr + (uint32_t)cb));
-      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-      if (my_row < N) {
-        float* dst = Dout + (size_t)my_row * ld + col0 + cb;
-#pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          float o[4];
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const int col = col0 + cb + j + u;
-            float v = na + sNb[cb + j + u] - 2.0f * __uint_as_float(r[j + u]);
-            if (col == my_row) v = INFINITY;   // self is never a neighbour
-            o[u] = v;
+          for (int q = 0; q < kChunkK / 8; ++q) {
+            const uint32_t a_addr = smem_u32(sA) + (uint32_t)((c * (kChunkK / 4) + q * 2) * (kTileM * 16));
+            const uint64_t adesc = make_smem_desc(a_addr, kTileM * 16, 128);
+            const uint64_t bdesc = make_smem_desc(b_addr + q * 2 * (kTileN * 16), kTileN * 16, 128);
+            const uint32_t accumulate = (c > 0 || q > 0) ? 1u : 0u;
+            asm volatile(
+                "{\n"
+                ".reg .pred p;\n"
+                "setp.ne.b32 p, %4, 0;\n"
+                "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+                "}\n" ::"r"(d_tmem),
+                "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate));
           }
-          if (col0 + cb + j + 3 < ld) *reinterpret_cast<float4*>(dst + j) = make_float4(o[0], o[1], o[2], o[3]);
+          // frees the ring slot once the MMAs that read it have completed
+          asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.b64 [%0];" ::"r"(smem_u32(&bar_empty[st]))
+                       : "memory");
         }
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.b64 [%0];" ::"r"(smem_u32(&bar_tfull[b]))
+                     : "memory");
       }
     }
-    asm volatile("tcgen05.fence::before_thread_sync;");
-    __syncthreads();   // all TMEM reads done before the next tile's MMAs overwrite the accumulator
-    asm volatile("tcgen05.fence::after_thread_sync;");
+  } else {
+    // ---- epilogue warps 0-7: warp w reads TMEM lanes [32(w%4), +32) = tile rows, column half w/4 ----
+    const int quarter = warp & 3, half = warp >> 2;
+    const int my_row = row0 + quarter * 32 + lane;
+    const float na = my_row < N ? norms[my_row] : 0.f;
+    const bool wide = (ld % 8 == 0) && (reinterpret_cast<uintptr_t>(Dout) % 32 == 0);
+    int t = 0;
+    for (int ct = blockIdx.y; ct < n_col_tiles; ct += gridDim.y, ++t) {
+      const int b = t & 1, col0 = ct * kTileN;
+      float* nb = sNb + b * kTileN;
+      // nb was last read two tiles ago by these same warps; the named barrier orders those reads before the refill
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      nb[tid] = (col0 + tid < N) ? norms[col0 + tid] : 0.f;
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      mbar_wait(&bar_tfull[b], (uint32_t)(t >> 1) & 1u);
+      asm volatile("tcgen05.fence::after_thread_sync;");
+      const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(b * kTileN + half * 128);
+      float* drow = Dout + (size_t)my_row * ld + col0 + half * 128;
+      const float* nbh = nb + half * 128;
+      // software pipeline over the four 32-column blocks: the TMEM load of block i+1 is in flight while block i is
+      // finished and stored (tcgen05.wait::ld covers every outstanding load, so it sits right before the issue)
+      uint32_t ra[32], rb[32];
+      tmem_ld32(lane_addr, ra);
+      tmem_ld_wait();
+      tmem_ld32(lane_addr + 32u, rb);
+      epilogue_block(ra, na, nbh, drow, 0, col0 + half * 128, ld, my_row < N, wide);
+      tmem_ld_wait();
+      tmem_ld32(lane_addr + 64u, ra);
+      epilogue_block(rb, na, nbh, drow, 32, col0 + half * 128, ld, my_row < N, wide);
+      tmem_ld_wait();
+      tmem_ld32(lane_addr + 96u, rb);
+      epilogue_block(ra, na, nbh, drow, 64, col0 + half * 128, ld, my_row < N, wide);
+      tmem_ld_wait();
+      epilogue_block(rb, na, nbh, drow, 96, col0 + half * 128, ld, my_row < N, wide);
+      asm volatile("tcgen05.fence::before_thread_sync;");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bar_tempty[b]);   // 8 arrivals (one per epilogue warp) release the accumulator
+    }
   }
-  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kTileN));
+  asm volatile("tcgen05.fence::before_thread_sync;");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;");
+  if (warp == 0)
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(2 * kTileN));
 }
 
 // One CTA per codebook row: exact top-K from the approximate distance row.
+template <int NE>
 __global__ void __launch_bounds__(kSelThreads) nbr_select_kernel(const float* __restrict__ E,
                                                                  const float* __restrict__ norms,
                                                                  const float* __restrict__ Dapprox, int ld, int N,
@@ -185,19 +280,27 @@ __global__ void __launch_bounds__(kSelThreads) nbr_select_kernel(const float* __
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double* key = reinterpret_cast<double*>(smem_raw);                       // [kCandMax]
   int* cidx = reinterpret_cast<int*>(smem_raw + (size_t)kCandMax * 8);      // [kCandMax]
+  double* erd = reinterpret_cast<double*>(smem_raw + (size_t)kCandMax * 12);   // [kGemmMaxDim]
   __shared__ SelectSmem sm;
   __shared__ int n_cand, bad;
   const int r = blockIdx.x, tid = threadIdx.x;
   const float* drow = Dapprox + (size_t)r * ld;
-  float v[kSelNE];
+  float v[NE];
+  // element e of thread tid is column col_of(e): 128-bit loads (rows are 16-byte aligned, ld % 4 == 0)
 #pragma unroll
-  for (int e = 0; e < kSelNE; ++e) {
-    const int j = e * kSelThreads + tid;
-    v[e] = j < N ? -drow[j] : -INFINITY;   // negated: K-th smallest distance = K-th largest value (self is -inf)
+  for (int e4 = 0; e4 < NE / 4; ++e4) {
+    const int j = (e4 * kSelThreads + tid) * 4;
+    float4 f = make_float4(INFINITY, INFINITY, INFINITY, INFINITY);
+    if (j < ld) f = *reinterpret_cast<const float4*>(drow + j);
+    // negated: K-th smallest distance = K-th largest value (self is -inf)
+    v[4 * e4 + 0] = (j + 0 < N && j + 0 != r) ? -f.x : -INFINITY;
+    v[4 * e4 + 1] = (j + 1 < N && j + 1 != r) ? -f.y : -INFINITY;
+    v[4 * e4 + 2] = (j + 2 < N && j + 2 != r) ? -f.z : -INFINITY;
+    v[4 * e4 + 3] = (j + 3 < N && j + 3 != r) ? -f.w : -INFINITY;
   }
   float vmin = INFINITY, vmax = -INFINITY;
 #pragma unroll
-  for (int e = 0; e < kSelNE; ++e) {
+  for (int e = 0; e < NE; ++e) {
     if (v[e] > -INFINITY) vmin = fminf(vmin, v[e]);
     vmax = fmaxf(vmax, v[e]);
   }
@@ -206,10 +309,10 @@ __global__ void __launch_bounds__(kSelThreads) nbr_select_kernel(const float* __
   // tier 2/3 selectors expect finite extremes; -inf entries (self, padding) simply rank last
   float kth;
   {
-    float tmp[kSelNE];
+    float tmp[NE];
 #pragma unroll
-    for (int e = 0; e < kSelNE; ++e) tmp[e] = v[e] > -INFINITY ? v[e] : vmin - 1.0f;
-    kth = select_slow<kSelNE>(tmp, K, vmin - 1.0f, vmax, sm);
+    for (int e = 0; e < NE; ++e) tmp[e] = v[e] > -INFINITY ? v[e] : vmin - 1.0f;
+    kth = select_slow<NE>(tmp, K, vmin - 1.0f, vmax, sm);
   }
   // error bound of the TF32 cross term + fp32 norms (see header): |D~ - d^2| <= eps
   const float na = sqrtf(norms[r]);
@@ -218,8 +321,8 @@ __global__ void __launch_bounds__(kSelThreads) nbr_select_kernel(const float* __
   if (tid == 0) { n_cand = 0; bad = 0; }
   __syncthreads();
 #pragma unroll
-  for (int e = 0; e < kSelNE; ++e) {
-    const int j = e * kSelThreads + tid;
+  for (int e = 0; e < NE; ++e) {
+    const int j = ((e >> 2) * kSelThreads + tid) * 4 + (e & 3);
     if (j < N && j != r && -v[e] <= cut) {
       const int p = atomicAdd(&n_cand, 1);
       if (p < kCandMax) cidx[p] = j;
@@ -234,15 +337,36 @@ __global__ void __launch_bounds__(kSelThreads) nbr_select_kernel(const float* __
   int np = 1;
   while (np < nc) np <<= 1;
   // exact squared distances of the candidates, oracle arithmetic (fp64, dimension order, no contraction)
+  // The query row is staged once as fp64; each thread then streams its candidate's row with 128-bit loads (the
+  // accumulation order over the dimensions is the oracle's, so the sum cannot be split across lanes).
   const float* er = E + (size_t)r * d;
+  for (int k = tid; k < d; k += kSelThreads) erd[k] = (double)er[k];
+  __syncthreads();
+  const bool vec4 = (d % 4 == 0) && (reinterpret_cast<uintptr_t>(E) % 16 == 0);
   for (int c = tid; c < np; c += kSelThreads) {
     if (c < nc) {
       const int j = cidx[c];
       const float* ej = E + (size_t)j * d;
       double acc = 0.0;
-      for (int k = 0; k < d; ++k) {
-        const double diff = __dsub_rn((double)er[k], (double)ej[k]);
-        acc = __dadd_rn(acc, __dmul_rn(diff, diff));
+      if (vec4) {
+        const float4* ej4 = reinterpret_cast<const float4*>(ej);
+#pragma unroll 4
+        for (int k4 = 0; k4 < d / 4; ++k4) {
+          const float4 f = __ldg(ej4 + k4);
+          double diff = __dsub_rn(erd[4 * k4 + 0], (double)f.x);
+          acc = __dadd_rn(acc, __dmul_rn(diff, diff));
+          diff = __dsub_rn(erd[4 * k4 + 1], (double)f.y);
+          acc = __dadd_rn(acc, __dmul_rn(diff, diff));
+          diff = __dsub_rn(erd[4 * k4 + 2], (double)f.z);
+          acc = __dadd_rn(acc, __dmul_rn(diff, diff));
+          diff = __dsub_rn(erd[4 * k4 + 3], (double)f.w);
+          acc = __dadd_rn(acc, __dmul_rn(diff, diff));
+        }
+      } else {
+        for (int k = 0; k < d; ++k) {
+          const double diff = __dsub_rn(erd[k], (double)ej[k]);
+          acc = __dadd_rn(acc, __dmul_rn(diff, diff));
+        }
       }
       key[c] = acc;
       if (fabs(acc - (double)drow[j]) > (double)eps) bad = 1;   // the bound must hold, otherwise D~ is not trustworthy
@@ -284,26 +408,41 @@ __global__ void max_norm_kernel(const float* __restrict__ norms, int N, float* _
 
 using namespace lantern;
 
+// norms must already hold |e_i|^2.  Packs E, then runs the persistent GEMM; D is fp32 [N, ld].
+static int launch_dist_gemm(const float* E_dev, const float* norms, int N, int d, float* D, int ld, cudaStream_t s) {
+  const int dpad = (d + kChunkK - 1) / kChunkK * kChunkK;
+  const int Npad = (N + kTileN - 1) / kTileN * kTileN;
+  uint32_t* Epk = nullptr;
+  LANTERN_CUDA(cudaMallocAsync(&Epk, (size_t)Npad * dpad * 4, s));
+  pack_tf32_kernel<<<2 * kNumSMs, 256, 0, s>>>(E_dev, N, d, Npad, dpad, Epk);
+  const size_t a_bytes = (size_t)dpad * kTileM * 4, stage = (size_t)kChunkK * kTileN * 4, tail = 2 * kTileN * 4;
+  const size_t budget = 227 * 1024 - 512;   // static shared memory (barriers) comes out of the same 227 KiB
+  const int n_stages = (int)std::min<size_t>(kMaxStages, (budget - a_bytes - tail) / stage);
+  const size_t smem = a_bytes + n_stages * stage + tail;   // > 113 KiB always: one CTA (and one 512-column TMEM allocation) per SM
+  LANTERN_CUDA(cudaFuncSetAttribute(dist_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int row_blocks = (N + kTileM - 1) / kTileM, col_tiles = (N + kTileN - 1) / kTileN;
+  const int gy = std::max(1, std::min(col_tiles, kNumSMs / row_blocks));
+  dist_gemm_kernel<<<dim3(row_blocks, gy), kGemmThreads, smem, s>>>(Epk, norms, N, Npad, dpad, n_stages, D, ld);
+  cudaError_t e = cudaGetLastError();
+  cudaFreeAsync(Epk, s);
+  LANTERN_CUDA(e);
+  return LANTERN_OK;
+}
+
 // Debug / test hook: the approximate distance matrix alone (fp32 [N, ld], ld = N rounded up to 4).
 extern "C" LANTERN_API int lantern_debug_dist_gemm(const float* E_dev, int32_t N, int32_t d, float* D_dev, int32_t ld,
                                                    void* stream) {
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  if (!E_dev || !D_dev || N < 2 || d < 1 || ld < N || ld % 4) {
+  if (!E_dev || !D_dev || N < 2 || d < 1 || d > kGemmMaxDim || ld < N || ld % 4) {
     set_error("lantern_debug_dist_gemm: bad argument");
     return LANTERN_E_INVALID;
   }
   float* norms = nullptr;
   LANTERN_CUDA(cudaMallocAsync(&norms, (size_t)N * 4, s));
   row_norms_kernel<<<(N + 255) / 256, 256, 0, s>>>(E_dev, N, d, norms);
-  const size_t smem = (size_t)kChunkK * (kTileM + kTileN) * 4 + kTileN * 4;
-  LANTERN_CUDA(cudaFuncSetAttribute(dist_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const int row_blocks = (N + kTileM - 1) / kTileM, col_tiles = (N + kTileN - 1) / kTileN;
-  const int gy = std::max(1, std::min(col_tiles, (2 * kNumSMs + row_blocks - 1) / row_blocks));
-  dist_gemm_kernel<<<dim3(row_blocks, gy), kGemmThreads, smem, s>>>(E_dev, norms, N, d, D_dev, ld);
-  cudaError_t e = cudaGetLastError();
+  int rc = launch_dist_gemm(E_dev, norms, N, d, D_dev, ld, s);
   cudaFreeAsync(norms, s);
-  LANTERN_CUDA(e);
-  return LANTERN_OK;
+  return rc;
 }
 
 // Returns LANTERN_OK and *fell_back = 0 when the tensor-core path produced the table, *fell_back = 1 when the caller
@@ -311,8 +450,8 @@ extern "C" LANTERN_API int lantern_debug_dist_gemm(const float* E_dev, int32_t N
 int build_neighbors_tensor_core(const float* E_dev, int N, int d, int K, int32_t* out_dev, cudaStream_t s,
                                 int* fell_back) {
   *fell_back = 1;
-  if (N > kSelNE * kSelThreads || K > kCandMax / 2 || K * 2 > N) return LANTERN_OK;
-  const int ld = (N + 3) & ~3;
+  if (N > kSelNE * kSelThreads || K > kCandMax / 2 || K * 2 > N || d > kGemmMaxDim) return LANTERN_OK;
+  const int ld = (N + 7) & ~7;   // rows start on 32-byte sectors (256-bit epilogue stores)
   float *norms = nullptr, *D = nullptr, *mx = nullptr;
   int* flags = nullptr;
   {   // keep the (up to 1 GiB) scratch in the stream-ordered pool between calls instead of returning it to the OS
@@ -334,18 +473,21 @@ int build_neighbors_tensor_core(const float* E_dev, int N, int d, int K, int32_t
   if (timing) cudaEventRecord(ev[0], s);
   row_norms_kernel<<<(N + 255) / 256, 256, 0, s>>>(E_dev, N, d, norms);
   max_norm_kernel<<<1, 512, 0, s>>>(norms, N, mx);
-  const size_t smem = (size_t)kChunkK * (kTileM + kTileN) * 4 + kTileN * 4;
-  LANTERN_CUDA(cudaFuncSetAttribute(dist_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const int row_blocks = (N + kTileM - 1) / kTileM, col_tiles = (N + kTileN - 1) / kTileN;
-  const int gy = std::max(1, std::min(col_tiles, (2 * kNumSMs + row_blocks - 1) / row_blocks));
-  dist_gemm_kernel<<<dim3(row_blocks, gy), kGemmThreads, smem, s>>>(E_dev, norms, N, d, D, ld);
+  { int rc = launch_dist_gemm(E_dev, norms, N, d, D, ld, s); if (rc != LANTERN_OK) return rc; }
   if (timing) cudaEventRecord(ev[1], s);
   float h_mx = 0.f;
   LANTERN_CUDA(cudaMemcpyAsync(&h_mx, mx, 4, cudaMemcpyDeviceToHost, s));
   LANTERN_CUDA(cudaStreamSynchronize(s));
-  const size_t sel_smem = (size_t)kCandMax * 12;
-  LANTERN_CUDA(cudaFuncSetAttribute(nbr_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sel_smem));
-  nbr_select_kernel<<<N, kSelThreads, sel_smem, s>>>(E_dev, norms, D, ld, N, d, K, h_mx, out_dev, flags);
+  const size_t sel_smem = (size_t)kCandMax * 12 + (size_t)kGemmMaxDim * 8;
+  auto run_select = [&](auto kern) -> cudaError_t {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sel_smem);
+    if (e != cudaSuccess) return e;
+    kern<<<N, kSelThreads, sel_smem, s>>>(E_dev, norms, D, ld, N, d, K, h_mx, out_dev, flags);
+    return cudaGetLastError();
+  };
+  if (N <= 8 * kSelThreads) LANTERN_CUDA(run_select(nbr_select_kernel<8>));
+  else if (N <= 16 * kSelThreads) LANTERN_CUDA(run_select(nbr_select_kernel<16>));
+  else LANTERN_CUDA(run_select(nbr_select_kernel<kSelNE>));
   if (timing) cudaEventRecord(ev[2], s);
   int h_flags[2] = {0, 0};
   LANTERN_CUDA(cudaMemcpyAsync(h_flags, flags, 8, cudaMemcpyDeviceToHost, s));

@@ -54,6 +54,8 @@ def parse():
     ap.add_argument("--cpu-items", type=int, default=0, help="items in the CPU sample (0 = auto)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-torch", action="store_true", help="skip the GPU-PyTorch baseline (reference op sequence)")
+    ap.add_argument("--torch-items", type=int, default=8, help="prompts in the GPU-PyTorch baseline sample")
     ap.add_argument("--no-lazy", action="store_true", help="skip the lazy-statistics side measurement")
     ap.add_argument("--no-graph", action="store_true", help="plain launches instead of CUDA-graph replay")
     return ap.parse_args()
@@ -442,10 +444,42 @@ def run_b200(args):
             line["cpu_baseline"] = {"value": v, "unit": "images/s", "cores": cores, "kind": "port",
                                     "sample": f"{n_items} prompts x 2 verify steps of the same workload, "
                                               f"oracle/lantern_oracle.py eager, one process per core ({wall:.1f}s wall)"}
+        if not args.no_torch and world == 1:
+            line["torch_gpu_baseline"] = torch_gpu_baseline(args, fam, batches[0], results and run(0), table_np, k, tpi)
         print(json.dumps(line))
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def torch_gpu_baseline(args, fam, bt, ours, table_np, k, tpi):
+    """SURVEY 8(d) "GPU-PyTorch path": the reference's own op sequence (small ATen kernels + host syncs, table rows
+    copied from numpy per candidate) on the same device inputs, one prompt at a time like the reference (batch 1)."""
+    import torch
+    from oracle import lantern_oracle as O, torch_path as TP
+    ofam = {"llamagen": O.LLAMAGEN, "anole": O.ANOLE, "lumina_mgpt": O.LUMINA}[args.family]
+    warp = O.Warp(1.0, 1.0, args.top_k)
+    n = min(args.torch_items, bt["cond"].shape[0])
+    uni = bt["uniforms"].cpu().numpy()
+
+    def one(b):
+        return TP.verify_step(bt["cond"][b], bt["uncond"][b], args.cfg, bt["tokens"][b], bt["retrieve"][b], uni[b],
+                              ofam, warp, True, k, args.lantern_delta, table_np)
+    one(0)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    outs = [one(b) for b in range(n)]
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    tokens = sum(o[1] + 1 for o in outs)
+    agree = None
+    if ours:
+        al = ours.accept_length.cpu().numpy()
+        tk = ours.token.cpu().numpy()
+        agree = int(sum(int(al[b]) == outs[b][1] and int(tk[b]) == outs[b][2] for b in range(n)))
+    return {"value": tokens / dt / tpi, "unit": "images/s", "ms_per_prompt_step": 1e3 * dt / n,
+            "sample": f"{n} prompts x 1 verify step of batch 0, oracle/torch_path.py on cuda (reference op sequence, batch 1)",
+            "same_accept_and_token_as_b200": None if agree is None else f"{agree}/{n}"}
 
 
 def run_e2e(args, fam, ver, table_np, tree_pool, rank, dev, world):

@@ -159,6 +159,16 @@ LANTERN_API int lantern_accept_phases(const lantern_accept_cfg* cfg, const lante
                                       void* stream, int phases);
 
 /*
+ * Glue for the reference's evaluate_posterior signature (drafters/utils.py:333, ea_model_llamagen.py:709), which
+ * receives `candidates [L, D]` (int64, -1 padded; token of node retrieve_indices[j, i]) instead of the tree's token
+ * vector: writes tree_tokens [n_rows] int32 (0 for unreachable nodes) and the int32 copy of retrieve_indices
+ * [n_paths, depth] that lantern_accept_fused consumes.  One memset + one launch, no host synchronisation.
+ */
+LANTERN_API int lantern_tree_from_candidates(const int64_t* cand_dev, const int64_t* retrieve_dev, int32_t n_paths,
+                                             int32_t depth, int32_t n_rows, int32_t* tokens_dev,
+                                             int32_t* retrieve32_dev, void* stream);
+
+/*
  * Bonus-token draw from caller-supplied probability rows (update_inference_inputs given a
  * sample_p that did not come from lantern_accept_fused): token[b] = min{i : cdf_i > u[b] * total}.
  * Replaces torch.multinomial(prob, 1) at ea_model_llamagen.py:978, ea_model_lumina_mgpt.py:781.

@@ -22,6 +22,7 @@ EXPORTS = (
     "lantern_accept_phases",
     "lantern_sample_tokens", "lantern_kv_compact", "lantern_build_neighbors", "lantern_philox_uniforms",
     "lantern_session_create", "lantern_session_step", "lantern_session_destroy", "lantern_debug_dist_gemm", "lantern_debug_neighbors_path", "lantern_build_dynamic_tree", "lantern_draft_sample",
+    "lantern_tree_from_candidates",
 )
 
 
@@ -110,6 +111,9 @@ def load() -> C.CDLL:
                                          C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
     lib.lantern_build_dynamic_tree.restype = C.c_int
     lib.lantern_build_dynamic_tree.argtypes = [C.c_void_p] * 4 + [C.c_int32] * 7 + [C.c_void_p] * 7
+    lib.lantern_tree_from_candidates.restype = C.c_int
+    lib.lantern_tree_from_candidates.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,
+                                                 C.c_void_p, C.c_void_p]
     lib.lantern_philox_uniforms.restype = None
     lib.lantern_philox_uniforms.argtypes = [C.c_uint64, C.c_uint64, C.c_uint32, C.c_int32, C.c_void_p]
     lib.lantern_session_create.restype = C.c_int

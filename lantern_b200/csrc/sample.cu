@@ -39,7 +39,37 @@ __global__ void __launch_bounds__(kSampleThreads) sample_tokens_kernel(const flo
   if (tid == 0) tokens[blockIdx.x] = found != 0x7fffffff ? found : (last_nz >= 0 ? last_nz : 0);
 }
 
+// The reference's evaluate_posterior receives `candidates [L, D]` (token of node retrieve_indices[j, i], -1 padded,
+// int64) rather than the tree's token vector; this rebuilds the kernel-side inputs in one launch:
+// tree_tokens[node] (int32, 0 for nodes no path reaches) and the int32 copy of retrieve_indices.
+__global__ void tree_from_candidates_kernel(const int64_t* __restrict__ cand, const int64_t* __restrict__ ri, int n,
+                                            int T, int32_t* __restrict__ tokens, int32_t* __restrict__ ri32) {
+  // tokens was zeroed by the memset the host enqueued before this launch
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const int64_t node = ri[i];
+    ri32[i] = (int32_t)node;
+    if (node >= 0 && node < T) tokens[node] = (int32_t)cand[i];   // every path through a node carries the same token
+  }
+}
+
 }  // namespace lantern
+
+extern "C" int lantern_tree_from_candidates(const int64_t* cand_dev, const int64_t* retrieve_dev, int32_t n_paths,
+                                            int32_t depth, int32_t n_rows, int32_t* tokens_dev, int32_t* retrieve32_dev,
+                                            void* stream) {
+  using namespace lantern;
+  if (!cand_dev || !retrieve_dev || !tokens_dev || !retrieve32_dev || n_paths <= 0 || depth <= 0 || n_rows <= 0) {
+    set_error("lantern_tree_from_candidates: bad argument");
+    return LANTERN_E_INVALID;
+  }
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  LANTERN_CUDA(cudaMemsetAsync(tokens_dev, 0, (size_t)n_rows * 4, s));
+  const int n = n_paths * depth;
+  tree_from_candidates_kernel<<<(n + 255) / 256, 256, 0, s>>>(cand_dev, retrieve_dev, n, n_rows, tokens_dev,
+                                                            retrieve32_dev);
+  LANTERN_CUDA(cudaGetLastError());
+  return LANTERN_OK;
+}
 
 extern "C" int lantern_sample_tokens(const float* probs_dev, int64_t row_stride, int32_t n_rows, int32_t vocab,
                                      const float* uniforms_dev, int32_t* tokens_dev, void* stream) {

@@ -178,22 +178,50 @@ def _draw_python_uniforms(n: int):
     return state, u
 
 
+class _HostIO:
+    """Per-device staging for the batch-1 drop-in call: pinned host buffers for the uniforms going in and the five
+    result integers coming out, so that one call costs two async copies and a single stream synchronisation."""
+
+    def __init__(self, device):
+        self.u_host = torch.empty(4096, dtype=torch.float32).pin_memory()
+        self.u_np = self.u_host.numpy()
+        self.u_dev = torch.empty(4096, dtype=torch.float32, device=device)
+        self.r_host = torch.zeros(8, dtype=torch.int32).pin_memory()
+        self.r_np = self.r_host.numpy()
+
+
+_host_io = {}
+
+
+def _io(device) -> _HostIO:
+    key = str(device)
+    io = _host_io.get(key)
+    if io is None:
+        io = _host_io[key] = _HostIO(device)
+    return io
+
+
 def _verify(fam: FamilySpec, logits, candidates: torch.Tensor, *, temp=1.0, top_p=1.0, top_k=0, lantern=False,
             lantern_k=1000, lantern_delta=0.1, nearest_latents=None, static_inputs=None, rng="python",
             philox=(0, 0), want_sample_p=True):
     """Returns (best_candidate 0-d int64 CPU tensor, accept_length int, sample_p [V] with ``_lantern_token``)."""
     fused = isinstance(logits, TreeLogits)
     device = logits.device
-    cand = candidates.to(device)
+    cand = candidates if candidates.device == device else candidates.to(device)
     L, D = cand.shape
+    stream = torch.cuda.current_stream(device)
     if fused:
         cond, uncond, cfg_scale = logits.cond, logits.uncond, logits.cfg_scale
-        ri64 = logits.retrieve_indices.to(device)
+        ri64 = logits.retrieve_indices
+        if ri64.device != device or ri64.dtype != torch.int64 or not ri64.is_contiguous():
+            ri64 = ri64.to(device=device, dtype=torch.int64).contiguous()
+        if cand.dtype != torch.int64 or not cand.is_contiguous():
+            cand = cand.to(torch.int64).contiguous()
         T = cond.shape[1]
-        tokens = torch.zeros(T, dtype=torch.int32, device=device)
-        m = ri64 >= 0
-        tokens[ri64[m]] = cand[m].to(torch.int32)
-        retrieve = ri64.to(torch.int32).contiguous()[None]
+        ibuf = torch.empty(T + L * D, dtype=torch.int32, device=device)
+        tokens, retrieve = ibuf[:T].view(1, T), ibuf[T:].view(1, L, D)
+        _abi.check(_abi.load().lantern_tree_from_candidates(cand.data_ptr(), ri64.data_ptr(), L, D, T,
+                                                            tokens.data_ptr(), retrieve.data_ptr(), stream.cuda_stream))
         kinds = logits.row_kinds
         if fam.family_id == _abi.FAMILY_LUMINA:
             top_k = logits.top_k
@@ -206,7 +234,7 @@ def _verify(fam: FamilySpec, logits, candidates: torch.Tensor, *, temp=1.0, top_
         tokens = cand.reshape(-1).to(torch.int32)
         ids = torch.arange(T, device=device, dtype=torch.int32).view(L, D)
         retrieve = torch.where(cand >= 0, ids, torch.full_like(ids, -1)).contiguous()[None]
-        tokens = torch.where(tokens >= 0, tokens, torch.zeros_like(tokens))
+        tokens = torch.where(tokens >= 0, tokens, torch.zeros_like(tokens)).view(1, T).contiguous()
         kinds = None
     table, k = None, int(lantern_k)
     if lantern:
@@ -219,16 +247,24 @@ def _verify(fam: FamilySpec, logits, candidates: torch.Tensor, *, temp=1.0, top_
         static, node_q, draft_op, sib_tokens = static_inputs
         kw = dict(node_q=node_q, draft_op=draft_op, sib_tokens=sib_tokens)
     ver = _get_verifier(fam, temp, top_p, top_k, cfg_scale, lantern, k, lantern_delta, table, static, device)
+    io = _io(device)
     uniforms = None
     state = None
     if rng == "python":
         state, u = _draw_python_uniforms(T)
-        u.append(float(torch.rand(()).item()))          # bonus-token draw comes from torch's generator
-        uniforms = torch.tensor([u], dtype=torch.float64).to(torch.float32).to(device)
-    res = ver.step(cond, uncond, tokens.view(1, T).contiguous(), retrieve, row_kinds=kinds, uniforms=uniforms,
+        n_u = T + 1
+        if n_u > io.u_np.shape[0]:
+            raise ValueError(f"tree of {T} nodes exceeds the uniform staging buffer")
+        io.u_np[:T] = u                                   # float64 -> float32, round to nearest like torch
+        io.u_np[T] = float(torch.rand(()).item())         # bonus-token draw comes from torch's generator
+        uniforms = io.u_dev[:n_u].view(1, n_u)
+        uniforms.copy_(io.u_host[:n_u].view(1, n_u), non_blocking=True)
+    res = ver.step(cond, uncond, tokens, retrieve, row_kinds=kinds, uniforms=uniforms,
                    philox=philox, want_sample_p=want_sample_p, bonus_uniform_last=(rng == "python"), **kw)
-    host = torch.stack([res.accept_length[0], res.best_candidate[0], res.token[0], res.n_draws[0]]).cpu()
-    a, best, token, draws = (int(x) for x in host)
+    # accept_length, best_candidate, token, n_draws, flags are the first five ints of one buffer (B = 1)
+    io.r_host[:5].copy_(res.ints[:5], non_blocking=True)
+    stream.synchronize()
+    a, best, token, draws = (int(x) for x in io.r_np[:4])
     if state is not None:                                # advance the module RNG exactly like the reference
         random.setstate(state)
         for _ in range(draws - 1):

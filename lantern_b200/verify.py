@@ -104,6 +104,7 @@ class Verifier:
             if not (1 <= self.lantern_k <= self.nbr_table.shape[1]):
                 raise ValueError(f"lantern_k={self.lantern_k} outside [1, {self.nbr_table.shape[1]}]")
         self._work = None
+        self._cfg_cache = {}
         self._out_cache = {}
 
     def _as_table(self, t) -> torch.Tensor:
@@ -168,7 +169,15 @@ class Verifier:
             if uniforms.dtype != torch.float32 or not uniforms.is_contiguous() or uniforms.shape[0] != B:
                 raise ValueError("uniforms must be contiguous fp32 [B, n]")
             n_uni = uniforms.shape[1]
-        cfg = self._cfg(B, T, L, D, logits_cond, shared, n_uni, philox)
+        ckey = (B, T, L, D, logits_cond.dtype, logits_cond.stride(0), logits_cond.stride(1), shared, n_uni)
+        cached = self._cfg_cache.get(ckey)
+        if cached is None:
+            cfg = self._cfg(B, T, L, D, logits_cond, shared, n_uni, philox)
+            if len(self._cfg_cache) > 32:
+                self._cfg_cache.clear()
+            cached = self._cfg_cache[ckey] = (cfg, int(self.lib.lantern_accept_workspace_bytes(C.byref(cfg))))
+        cfg, need = cached
+        cfg.philox_seed, cfg.philox_step = int(philox[0]) & (2**64 - 1), int(philox[1]) & (2**64 - 1)
         cfg.bonus_uniform_last = int(bonus_uniform_last)
         ain = _abi.AcceptIn()
         ain.logits_cond, ain.logits_uncond = _ptr(logits_cond), _ptr(logits_uncond)
@@ -193,13 +202,13 @@ class Verifier:
         res = VerifyResult(ints[0:B], ints[B:2 * B], ints[2 * B:3 * B],
                            ints[5 * B:5 * B + B * D].view(B, D), ints[5 * B + B * D:].view(B, D),
                            ints[3 * B:4 * B], ints[4 * B:5 * B])
+        res.ints = ints      # [accept_length | best_candidate | token | n_draws | flags] x B, then the two [B, D] tables
         if want_sample_p:
             res.sample_p = torch.empty(B, V, dtype=torch.float32, device=dev)
         aout = _abi.AcceptOut()
         aout.accept_length, aout.best_candidate, aout.token = _ptr(res.accept_length), _ptr(res.best_candidate), _ptr(res.token)
         aout.path_tokens, aout.select_indices = _ptr(res.path_tokens), _ptr(res.select_indices)
         aout.n_draws, aout.flags, aout.sample_p = _ptr(res.n_draws), _ptr(res.flags), _ptr(res.sample_p)
-        need = self.lib.lantern_accept_workspace_bytes(C.byref(cfg))
         if self._work is None or self._work.numel() < need or self._work.device != dev:
             self._work = torch.empty(max(need, 1), dtype=torch.uint8, device=dev)
         stream = torch.cuda.current_stream(dev).cuda_stream

@@ -152,8 +152,11 @@ LANTERN_API int lantern_accept_fused(const lantern_accept_cfg* cfg, const lanter
                          const lantern_accept_out* out, void* workspace_dev, size_t workspace_bytes,
                          void* stream);
 
-/* Measurement hook: the same step restricted to some phases (bit 0: per-row statistics kernel, bit 1: walk
- * kernel).  bench.py uses it to time the HBM-bound kernel on its own; phases == 3 is lantern_accept_fused. */
+/* The same step with an explicit schedule.  phases bit 0: per-row statistics kernel over every tree row (streamed,
+ * HBM-bound); bit 1: walk kernel; bit 2: lazy - the walk computes the statistics of the rows it visits itself (no
+ * streamed kernel; needs a 4096/8192/16384/32768-column window and no top-p); bit 3: automatic - streamed below
+ * 2048 tree rows in the batch, lazy from there on when eligible.  3 is lantern_accept_fused, 6 lazy, 8 automatic,
+ * 1 times the HBM-bound kernel on its own (bench.py).  Results are identical in every schedule. */
 LANTERN_API int lantern_accept_phases(const lantern_accept_cfg* cfg, const lantern_accept_in* in,
                                       const lantern_accept_out* out, void* workspace_dev, size_t workspace_bytes,
                                       void* stream, int phases);

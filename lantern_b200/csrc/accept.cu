@@ -38,59 +38,22 @@ constexpr int kMaxSib = 64;
 template <int DT>
 __host__ __device__ constexpr int cfg_ncols_bytes(int ncols) { return ncols * Elem<DT>::kBytes; }
 
-// MODE 0: generic (bounds-checked, runtime CFG switch, -inf aware statistics).
-// MODE 1: fast path: vector loads, ncols == 4*NT*NQ exactly, CFG-mixed input (logits_uncond present).
-// MODE 2: fast path without logits_uncond.
-template <int DT, int NT, int NQ, bool VEC, int MODE>
-__global__ void __launch_bounds__(NT, (MODE != 0 ? (NT <= 512 ? 2 : 1) : (NQ <= 8 ? 1024 / NT : 512 / NT)))
-    row_stats_kernel(const AcceptParams P) {
+// Generic row-statistics kernel: any window width up to NT * NQ * 4 columns, bounds-checked loads, runtime CFG
+// switch, -inf aware statistics.  The TMA-staged kernel for the power-of-two windows lives in stats_fast.cuh.
+template <int DT, int NT, int NQ, bool VEC>
+__global__ void __launch_bounds__(NT, (NQ <= 8 ? 1024 / NT : 512 / NT)) row_stats_kernel(const AcceptParams P) {
   constexpr int NE = NQ * 4;
   constexpr int NW = NT / 32;
-  constexpr bool FAST = MODE != 0;
   __shared__ SelectSmem sm;
   __shared__ float fscratch[33];
-  __shared__ __align__(8) uint64_t mbar;
-  // dynamic shared memory: [staged cond row][staged uncond row] (fast modes) then the [NE][NT] parking columns
-  extern __shared__ __align__(128) unsigned char dyn_smem[];
-  const int stage_bytes = FAST ? ((cfg_ncols_bytes<DT>(P.cfg.ncols) + 32 + 127) & ~127) : 0;
-  unsigned char* buf_c = dyn_smem;
-  unsigned char* buf_u = dyn_smem + stage_bytes;
-  float* park = reinterpret_cast<float*>(dyn_smem + (MODE == 1 ? 2 : (MODE == 2 ? 1 : 0)) * stage_bytes);
+  extern __shared__ __align__(128) unsigned char dyn_smem[];   // the [NE][NT] parking columns of the bracket select
+  float* park = reinterpret_cast<float*>(dyn_smem);
 
   const lantern_accept_cfg& cfg = P.cfg;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const long long n_rows_total = (long long)cfg.n_items * cfg.n_rows;
-  const bool has_uncond = MODE == 1 || (MODE == 0 && P.mix.has_uncond);
-  MixParams mix = P.mix;
-  mix.has_uncond = has_uncond;
-  constexpr int EB = Elem<DT>::kBytes;
-
-  // fast modes: single-buffer TMA pipeline.  Thread 0 issues the bulk copies of a row; the copy of row r+grid is
-  // issued as soon as row r has been lifted into registers, so it overlaps all of row r's arithmetic.
-  auto issue_row = [&](long long r) {
-    const int64_t rb = (r / cfg.n_rows) * cfg.item_stride + (r % cfg.n_rows) * cfg.row_stride + cfg.col0;
-    const uintptr_t gc = reinterpret_cast<uintptr_t>(P.in.logits_cond) + (uintptr_t)rb * EB;
-    const uintptr_t ac = gc & ~uintptr_t(15);
-    const uint32_t bc = (uint32_t)((gc - ac) + (uintptr_t)cfg.ncols * EB + 15) & ~15u;
-    uint32_t bu = 0;
-    uintptr_t au = 0;
-    if (MODE == 1) {
-      const uintptr_t gu = reinterpret_cast<uintptr_t>(P.in.logits_uncond) + (uintptr_t)rb * EB;
-      au = gu & ~uintptr_t(15);
-      bu = (uint32_t)((gu - au) + (uintptr_t)cfg.ncols * EB + 15) & ~15u;
-    }
-    mbar_expect_tx(&mbar, bc + bu);
-    bulk_g2s(buf_c, reinterpret_cast<const void*>(ac), bc, &mbar);
-    if (MODE == 1) bulk_g2s(buf_u, reinterpret_cast<const void*>(au), bu, &mbar);
-  };
-  uint32_t parity = 0;
-  if (FAST) {
-    if (tid == 0) {
-      mbar_init(&mbar, 1);
-      if ((long long)blockIdx.x < n_rows_total) issue_row(blockIdx.x);
-    }
-    __syncthreads();
-  }
+  const MixParams mix = P.mix;
+  const bool has_uncond = mix.has_uncond;
 
   for (long long row = blockIdx.x; row < n_rows_total; row += gridDim.x) {
     const int b = (int)(row / cfg.n_rows), t = (int)(row % cfg.n_rows);
@@ -98,13 +61,13 @@ __global__ void __launch_bounds__(NT, (MODE != 0 ? (NT <= 512 ? 2 : 1) : (NQ <= 
     st.thr = -INFINITY; st.mx = 0.f; st.sum = 1.f; st.vcut = -INFINITY; st.icut = -1;
     st.kind = P.in.row_kinds ? (int)P.in.row_kinds[row] : LANTERN_ROW_IMAGE;
     st.pad0 = st.pad1 = 0;
-    if (!FAST && st.kind != LANTERN_ROW_IMAGE) {   // one-hot rows: nothing to read
+    if (st.kind != LANTERN_ROW_IMAGE) {   // one-hot rows: nothing to read
       if (tid == 0) P.stats[row] = st;
       continue;
     }
     const int64_t base = (int64_t)b * cfg.item_stride + (int64_t)t * cfg.row_stride + cfg.col0;
-    // generic mode: pull the next row of this CTA towards L2 while this one is being processed
-    if (!FAST && tid == 0 && row + gridDim.x < n_rows_total) {
+    // pull the next row of this CTA towards L2 while this one is being processed
+    if (tid == 0 && row + gridDim.x < n_rows_total) {
       const long long nr = row + gridDim.x;
       const int64_t nbase = (nr / cfg.n_rows) * cfg.item_stride + (nr % cfg.n_rows) * cfg.row_stride + cfg.col0;
       const size_t eb = Elem<DT>::kBytes;
@@ -117,23 +80,13 @@ __global__ void __launch_bounds__(NT, (MODE != 0 ? (NT <= 512 ? 2 : 1) : (NQ <= 
         if (b1 > b0) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(b0), "r"((unsigned)(b1 - b0)));
       }
     }
-    float s[NE];
-    int lead_c = 0, lead_u = 0;   // bytes between the 16-byte aligned copy start and the first window element
-    if (FAST) {
-      lead_c = (int)((reinterpret_cast<uintptr_t>(P.in.logits_cond) + (uintptr_t)base * EB) & 15);
-      if (MODE == 1) lead_u = (int)((reinterpret_cast<uintptr_t>(P.in.logits_uncond) + (uintptr_t)base * EB) & 15);
-      mbar_wait(&mbar, parity);
-      parity ^= 1;
-    }
     // ---- lift the row into registers (fully unrolled) ----
+    float s[NE];
 #pragma unroll
     for (int q = 0; q < NQ; ++q) {
       const int e0 = (q * NT + tid) * 4;
       float c4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY}, u4[4] = {0.f, 0.f, 0.f, 0.f};
-      if (FAST) {
-        lds4<DT>(buf_c + lead_c, e0, c4);
-        if (MODE == 1) lds4<DT>(buf_u + lead_u, e0, u4);
-      } else if (VEC) {
+      if (VEC) {
         if (e0 < cfg.ncols) {
           Elem<DT>::load4(P.in.logits_cond, base + e0, c4);
           if (has_uncond) Elem<DT>::load4(P.in.logits_uncond, base + e0, u4);
@@ -150,26 +103,14 @@ __global__ void __launch_bounds__(NT, (MODE != 0 ? (NT <= 512 ? 2 : 1) : (NQ <= 
 #pragma unroll
       for (int j = 0; j < 4; ++j) s[q * 4 + j] = mix_temper(c4[j], u4[j], mix);   // padding: -inf stays -inf
     }
-    if (FAST) {
-      __syncthreads();   // every thread has consumed the staged row: the buffers may be overwritten
-      if (tid == 0 && row + gridDim.x < n_rows_total) issue_row(row + gridDim.x);
-      if (st.kind != LANTERN_ROW_IMAGE) {
-        if (tid == 0) P.stats[row] = st;
-        continue;
-      }
-    }
-    // ---- row statistics: sum, sum of squares, min, max (+ finite count), one fused two-level reduction ----
+    // ---- row statistics: sum, sum of squares, min, max, finite count; one fused two-level reduction ----
     float fsum = 0.f, fsq = 0.f, fmin_ = INFINITY, fmax_ = -INFINITY;
     int nfin = 0;
 #pragma unroll
     for (int e = 0; e < NE; ++e) {
       const float v = s[e];
       fmax_ = fmaxf(fmax_, v);
-      if (FAST) {            // no padding: masked (-inf) logits are caught below through a non-finite minimum
-        fsum += v;
-        fsq = fmaf(v, v, fsq);
-        fmin_ = fminf(fmin_, v);
-      } else if (v > -INFINITY) {
+      if (v > -INFINITY) {
         fsum += v;
         fsq = fmaf(v, v, fsq);
         fmin_ = fminf(fmin_, v);
@@ -180,7 +121,7 @@ __global__ void __launch_bounds__(NT, (MODE != 0 ? (NT <= 512 ? 2 : 1) : (NQ <= 
     fsq = warp_reduce(fsq, OpSum());
     fmin_ = -warp_reduce(-fmin_, OpMaxF());
     fmax_ = warp_reduce(fmax_, OpMaxF());
-    if (!FAST) nfin = __reduce_add_sync(0xffffffffu, nfin);
+    nfin = __reduce_add_sync(0xffffffffu, nfin);
     __syncthreads();
     if (lane == 0) {
       sm.f4[0][warp] = fsum; sm.f4[1][warp] = fsq; sm.f4[2][warp] = fmin_; sm.f4[3][warp] = fmax_;
@@ -198,7 +139,7 @@ __global__ void __launch_bounds__(NT, (MODE != 0 ? (NT <= 512 ? 2 : 1) : (NQ <= 
     }
     __syncthreads();
     fsum = sm.f_scr[2]; fsq = sm.f_scr[3]; fmin_ = sm.f_scr[4]; fmax_ = sm.f_scr[5];
-    nfin = FAST ? cfg.ncols : sm.i_scr[4];
+    nfin = sm.i_scr[4];
     const float m = fmax_;
     // ---- top-k threshold (exact k-th largest; ties are kept by the >= test below) ----
     if (P.do_topk) {
@@ -813,6 +754,13 @@ template <int DT, bool VEC>
 static int launch_all(const AcceptParams& P, cudaStream_t stream, int phases) {
   const lantern_accept_cfg& c = P.cfg;
   const long long rows = (long long)c.n_items * c.n_rows;
+  if (phases & 8) {
+    // automatic policy (measured, profiles/sweep_r1.md): streaming every tree row pays off while the step is
+    // latency-bound; from ~2K rows on, computing the statistics of the visited rows inside the walk is faster
+    const int ne = c.ncols / kWalkThreads;
+    const bool lazy_ok = VEC && !P.do_topp && c.ncols % (4 * kWalkThreads) == 0 && (ne == 4 || ne == 8 || ne == 16 || ne == 32);
+    phases = (lazy_ok && rows >= 2048) ? 6 : 3;
+  }
   const int nquads = (c.ncols + 3) / 4;
   // Thread/element split.  Generic mode: 256 threads up to 8192 columns, 512 beyond.  Fast (TMA-staged) modes:
   // 32 elements per thread (256 threads for 8192 columns, 512 for 16384): measured faster than 16 per thread
@@ -849,9 +797,9 @@ static int launch_all(const AcceptParams& P, cudaStream_t stream, int phases) {
   int per_sm = mode ? (nt <= 512 ? 2 : 1) : (nq_inst <= 8 ? 1024 / nt : 512 / nt);
   per_sm = std::max(1, std::min<int>(per_sm, (int)((227 * 1024) / (park_bytes + 5 * 1024))));
   const int grid = (int)std::min<long long>(rows, (long long)kNumSMs * per_sm);
-#define LAUNCH_STATS_MODE(NT, NQ, V, M)                                                                   \
+#define LAUNCH_STATS(NT, NQ)                                                                              \
   do {                                                                                                    \
-    auto kk = row_stats_kernel<DT, NT, NQ, V, M>;                                                         \
+    auto kk = row_stats_kernel<DT, NT, NQ, VEC>;                                                          \
     if (park_bytes > 48 * 1024)                                                                           \
       LANTERN_CUDA(cudaFuncSetAttribute(kk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)park_bytes)); \
     kk<<<grid, NT, park_bytes, stream>>>(P);                                                              \
@@ -868,7 +816,6 @@ static int launch_all(const AcceptParams& P, cudaStream_t stream, int phases) {
     if (mode == 1) LAUNCH_FAST_MODE(NT, NQ, 1); \
     else LAUNCH_FAST_MODE(NT, NQ, 2);           \
   } while (0)
-#define LAUNCH_STATS(NT, NQ) LAUNCH_STATS_MODE(NT, NQ, VEC, 0)
   if (!(phases & 1) || (phases & 4)) {
   } else if (mode) {
     if (nt == 256 && nq_inst == 2) LAUNCH_FAST(256, 2);
@@ -896,7 +843,6 @@ static int launch_all(const AcceptParams& P, cudaStream_t stream, int phases) {
   }
 #undef LAUNCH_FAST
 #undef LAUNCH_FAST_MODE
-#undef LAUNCH_STATS_MODE
 #undef LAUNCH_STATS
   LANTERN_CUDA(cudaGetLastError());
   if ((phases & 1) && !(phases & 4) && P.do_topp) {   // nucleus cut on top of the row statistics (slow path, one CTA per row)

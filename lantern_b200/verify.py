@@ -72,6 +72,11 @@ class VerifyResult:
     sample_p: Optional[torch.Tensor] = None   # [B, V] fp32
 
 
+# lantern_accept_phases schedules: every tree row streamed through the statistics kernel, statistics computed lazily
+# inside the walk, or chosen per batch by the library (profiles/sweep_r1.md)
+_SCHEDULES = {"streamed": 3, "lazy": 6, "auto": 8}
+
+
 def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
     return None if t is None else t.data_ptr()
 
@@ -82,8 +87,11 @@ class Verifier:
     def __init__(self, family: FamilySpec, *, temperature: float = 1.0, top_k: int = 0, top_p: float = 1.0,
                  cfg_scale: float = 1.0, lantern: bool = False, lantern_k: int = 1000, lantern_delta: float = 0.1,
                  nbr_table: Optional[torch.Tensor] = None, static_tree: Optional[StaticTree] = None,
-                 device: Optional[torch.device] = None):
+                 device: Optional[torch.device] = None, schedule: str = "streamed"):
         self.lib = _abi.load()
+        if schedule not in _SCHEDULES:
+            raise ValueError(f"schedule must be one of {sorted(_SCHEDULES)}")
+        self.schedule = schedule
         self.family = family
         self.temperature = float(temperature)
         self.top_k = int(top_k)
@@ -143,9 +151,11 @@ class Verifier:
              uniforms: Optional[torch.Tensor] = None, philox: Tuple[int, int] = (0, 0),
              node_q: Optional[torch.Tensor] = None, draft_op: Optional[torch.Tensor] = None,
              sib_tokens: Optional[torch.Tensor] = None, want_sample_p: bool = False,
-             phases: int = 3, bonus_uniform_last: bool = False) -> VerifyResult:
+             phases: Optional[int] = None, bonus_uniform_last: bool = False) -> VerifyResult:
         """logits_*: [B, T, V] (fp32/bf16/fp16, last dim contiguous); tree_tokens: [B, T] int32;
         retrieve: [B, L, D] or [L, D] int32 (defaults to the static tree's).  Asynchronous."""
+        if phases is None:
+            phases = _SCHEDULES[self.schedule]
         if logits_cond.dim() != 3 or logits_cond.stride(2) != 1:
             raise ValueError("logits must be [B, T, V] with a contiguous last dimension")
         if logits_uncond is not None and (logits_uncond.shape != logits_cond.shape

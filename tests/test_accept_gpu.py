@@ -220,6 +220,26 @@ def test_lazy_statistics_mode(family, kw):
     assert torch.equal(res.accept_length, eager.accept_length) and torch.equal(res.token, eager.token)
 
 
+def test_automatic_schedule_matches_both():
+    """phases = 8: the library picks streamed or lazy per batch; either way the results are the oracle's.  Covers a
+    window that is not lazy-eligible (2048 columns), a small batch (streamed) and one past the 2048-row switch."""
+    for kw, n in ((dict(family="llamagen", ncols=2048, top_k=300, lantern_k=100), 3),
+                  (dict(family="lumina_mgpt", ncols=4096, top_k=500, lantern_k=100, depth=5), 3),
+                  (dict(family="lumina_mgpt", ncols=4096, top_k=500, lantern_k=100, depth=5), 40)):
+        built, orcs, seed = [], [], 47000
+        while len(built) < min(n, 6):
+            b = C.build(dict(seed=seed, **kw))
+            seed += 1
+            o = C.oracle_step(b)
+            if o.margin >= MARGIN:
+                built.append(b)
+                orcs.append(o)
+        cases = [built[i % len(built)] for i in range(n)]      # 40 x 59 rows > 2048: the lazy side of the switch
+        res = R.run_cases(cases, phases=8)
+        for i in range(n):
+            R.compare(res, i, orcs[i % len(built)])
+
+
 def test_vanilla_llm_vocab_32000():
     """Plain EAGLE verification on an LLM-sized vocabulary (non power of two -> generic statistics kernel)."""
     built, orcs, seed = [], [], 52000

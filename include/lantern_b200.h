@@ -195,8 +195,15 @@ typedef struct lantern_kv_cfg {
   int32_t s_max;            /* max_position_embeddings */
   int32_t head_dim;
   int32_t max_keep;         /* row stride of `select` (D) */
+  /* Single-prompt shortcuts (the reference's batch-1 call): host scalars used where the matching device array
+   * argument is NULL, so the drop-in shim needs no host-to-device copy at all. */
+  void* slab0;              /* used when slab_ptrs_dev == NULL (n_slabs must be 1) */
+  int32_t prev_len0;        /* used for every item when prev_len_dev == NULL */
+  int32_t n_keep0;          /* used for every item when n_keep_dev == NULL */
+  int32_t select_i64;       /* != 0: `select_dev` holds int64 (torch.long) indices */
+  int32_t reserved0;
 } lantern_kv_cfg;
-LANTERN_API int lantern_kv_compact(const lantern_kv_cfg* cfg, void* const* slab_ptrs_dev, const int32_t* select_dev,
+LANTERN_API int lantern_kv_compact(const lantern_kv_cfg* cfg, void* const* slab_ptrs_dev, const void* select_dev,
                        const int32_t* prev_len_dev, const int32_t* n_keep_dev, void* stream);
 
 /*

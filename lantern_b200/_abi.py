@@ -65,6 +65,8 @@ class KvCfg(C.Structure):
         ("n_slabs", C.c_int32), ("elem_bytes", C.c_int32), ("n_outer", C.c_int64),
         ("outer_per_batch", C.c_int64), ("n_batch", C.c_int32), ("s_max", C.c_int32),
         ("head_dim", C.c_int32), ("max_keep", C.c_int32),
+        ("slab0", C.c_void_p), ("prev_len0", C.c_int32), ("n_keep0", C.c_int32), ("select_i64", C.c_int32),
+        ("reserved0", C.c_int32),
     ]
 
 

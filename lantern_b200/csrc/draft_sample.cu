@@ -11,22 +11,18 @@
 
 namespace lantern {
 
-constexpr int kDraftThreads = 512;
+constexpr int kDraftGroups = 8;   // 4-column groups per thread: a row of up to 32 * NT window columns stays in registers
 
-__device__ __forceinline__ double race_key(float p, uint64_t seed, uint64_t step, uint32_t row, uint32_t col) {
-  uint32_t c[4] = {col >> 2, static_cast<uint32_t>(step), row, static_cast<uint32_t>(step >> 32) ^ 0x5A17u};
-  philox4x32_10(c, static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32));
-  const double u = ((double)(c[col & 3] >> 8) + 1.0) * (1.0 / 16777216.0);   // (0, 1]
-  return -log(u) / (double)p;
-}
-
-template <int DT>
-__global__ void __launch_bounds__(kDraftThreads) draft_sample_kernel(const AcceptParams P, int k, float* probs_out,
-                                                                     int32_t* idx_out, float* cond_out) {
-  __shared__ double best_key[kDraftThreads / 32];
-  __shared__ int best_idx[kDraftThreads / 32];
-  __shared__ double last_key_s;
-  __shared__ int last_idx_s;
+// One CTA per drafter row.  Single pass over the row: probabilities (written out as `op`), one Philox call per four
+// columns, fp64 race keys kept in registers.  The k draws are then k block-wide argmins over (key, column) in which
+// only the thread that owned the previous winner rescans its registers.
+template <int DT, int NT>
+__global__ void __launch_bounds__(NT) draft_sample_kernel(const AcceptParams P, int k, float* probs_out,
+                                                          int32_t* idx_out, float* cond_out) {
+  constexpr int NG = kDraftGroups, NE = NG * 4, NW = NT / 32;
+  __shared__ double warp_key[NW];
+  __shared__ int warp_col[NW];
+  __shared__ int win_col;
   __shared__ float picked_p[64];
   const lantern_accept_cfg& cfg = P.cfg;
   const int row = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, V = cfg.vocab;
@@ -36,50 +32,113 @@ __global__ void __launch_bounds__(kDraftThreads) draft_sample_kernel(const Accep
   const MixParams mix = P.mix;
   const ExpShift ex(st.mx);
   const float inv = __fdiv_rn(1.0f, st.sum);
-  auto prob = [&](int e) -> float {
-    const float c = Elem<DT>::load1(P.in.logits_cond, base + e);
-    const float u = mix.has_uncond ? Elem<DT>::load1(P.in.logits_uncond, base + e) : 0.f;
-    const float s = mix_temper(c, u, mix);
-    return kept_col(s, e, st) ? __fmul_rn(ex(s), inv) : 0.f;
-  };
   float* prow = probs_out + (size_t)row * V;
-  for (int v = tid; v < V; v += kDraftThreads) {
-    const int e = v - cfg.col0;
-    prow[v] = (e >= 0 && e < cfg.ncols) ? prob(e) : 0.f;
-  }
-  if (tid == 0) { last_key_s = -1.0; last_idx_s = -1; }
-  __syncthreads();
-  for (int r = 0; r < k; ++r) {
-    const double lk = last_key_s;
-    const int li = last_idx_s;
-    double bk = INFINITY;
-    int bi = 0x7fffffff;
-    for (int e = tid; e < cfg.ncols; e += kDraftThreads) {
-      const float p = prow[e + cfg.col0];
-      if (p <= 0.f) continue;
-      const double key = race_key(p, cfg.philox_seed, cfg.philox_step, (uint32_t)row, (uint32_t)e);
-      const bool after = key > lk || (key == lk && e > li);   // strictly after the previous pick in (key, column) order
-      if (after && (key < bk || (key == bk && e < bi))) { bk = key; bi = e; }
+  // columns outside the image-token window carry no mass
+  for (int v = tid; v < cfg.col0; v += NT) prow[v] = 0.f;
+  for (int v = cfg.col0 + cfg.ncols + tid; v < V; v += NT) prow[v] = 0.f;
+  const bool vec_out = P.vec_ok && (reinterpret_cast<uintptr_t>(prow + cfg.col0) % 16 == 0);
+
+  double key[NE];
+  const uint32_t k0 = static_cast<uint32_t>(cfg.philox_seed), k1 = static_cast<uint32_t>(cfg.philox_seed >> 32);
+#pragma unroll
+  for (int g = 0; g < NG; ++g) {
+    const int e0 = (g * NT + tid) * 4;
+    float c4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY}, u4[4] = {0.f, 0.f, 0.f, 0.f};
+    if (e0 < cfg.ncols) {
+      if (P.vec_ok) {
+        Elem<DT>::load4(P.in.logits_cond, base + e0, c4);
+        if (mix.has_uncond) Elem<DT>::load4(P.in.logits_uncond, base + e0, u4);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if (e0 + j < cfg.ncols) {
+            c4[j] = Elem<DT>::load1(P.in.logits_cond, base + e0 + j);
+            if (mix.has_uncond) u4[j] = Elem<DT>::load1(P.in.logits_uncond, base + e0 + j);
+          }
+        }
+      }
     }
+    float p4[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float sv = mix_temper(c4[j], u4[j], mix);
+      p4[j] = (e0 + j < cfg.ncols && kept_col(sv, e0 + j, st)) ? __fmul_rn(ex(sv), inv) : 0.f;
+    }
+    if (e0 < cfg.ncols) {
+      if (vec_out) {
+        *reinterpret_cast<float4*>(prow + cfg.col0 + e0) = make_float4(p4[0], p4[1], p4[2], p4[3]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (e0 + j < cfg.ncols) prow[cfg.col0 + e0 + j] = p4[j];
+      }
+    }
+    // race keys: u = ((word >> 8) + 1) * 2^-24 in (0, 1], word (col & 3) of the Philox block of counter col / 4
+    uint32_t c[4] = {(uint32_t)(e0 >> 2), static_cast<uint32_t>(cfg.philox_step), (uint32_t)row,
+                     static_cast<uint32_t>(cfg.philox_step >> 32) ^ 0x5A17u};
+    const bool any = p4[0] > 0.f || p4[1] > 0.f || p4[2] > 0.f || p4[3] > 0.f;
+    if (any) philox4x32_10(c, k0, k1);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      double kk = INFINITY;
+      if (p4[j] > 0.f) {
+        const double u = ((double)(c[j] >> 8) + 1.0) * (1.0 / 16777216.0);
+        kk = -log(u) / (double)p4[j];
+      }
+      key[g * 4 + j] = kk;
+    }
+  }
+
+  // thread-local argmin; slots are visited in increasing column order, so `<` keeps the smallest column among ties
+  auto local_best = [&](double& bk, int& bc) {
+    bk = INFINITY;
+    bc = 0x7fffffff;
+#pragma unroll
+    for (int i = 0; i < NE; ++i) {
+      if (key[i] < bk) { bk = key[i]; bc = ((i >> 2) * NT + tid) * 4 + (i & 3); }
+    }
+  };
+  double my_key;
+  int my_col;
+  local_best(my_key, my_col);
+  for (int r = 0; r < k; ++r) {
+    double bk = my_key;
+    int bc = my_col;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
       const double ok = __shfl_xor_sync(0xffffffffu, bk, o);
-      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-      if (ok < bk || (ok == bk && oi < bi)) { bk = ok; bi = oi; }
+      const int oc = __shfl_xor_sync(0xffffffffu, bc, o);
+      if (ok < bk || (ok == bk && oc < bc)) { bk = ok; bc = oc; }
     }
-    if (lane == 0) { best_key[warp] = bk; best_idx[warp] = bi; }
+    if (lane == 0) { warp_key[warp] = bk; warp_col[warp] = bc; }
     __syncthreads();
-    if (tid == 0) {
-      for (int w = 1; w < kDraftThreads / 32; ++w)
-        if (best_key[w] < bk || (best_key[w] == bk && best_idx[w] < bi)) { bk = best_key[w]; bi = best_idx[w]; }
-      last_key_s = bk;
-      last_idx_s = bi;
-      const bool ok = bi != 0x7fffffff;   // fewer than k columns with positive probability: pad like torch would fail
-      idx_out[(size_t)row * k + r] = ok ? bi + cfg.col0 : -1;
-      picked_p[r] = ok ? prow[bi + cfg.col0] : 0.f;
+    if (warp == 0) {
+      bk = lane < NW ? warp_key[lane] : INFINITY;
+      bc = lane < NW ? warp_col[lane] : 0x7fffffff;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const double ok = __shfl_xor_sync(0xffffffffu, bk, o);
+        const int oc = __shfl_xor_sync(0xffffffffu, bc, o);
+        if (ok < bk || (ok == bk && oc < bc)) { bk = ok; bc = oc; }
+      }
+      if (lane == 0) win_col = bc;
     }
     __syncthreads();
+    const int wc = win_col;
+    const bool ok = wc != 0x7fffffff;   // fewer than k columns with positive probability: pad like torch would fail
+    if (ok && wc == my_col) {           // the owner retires the winner, reports it and rescans its registers
+#pragma unroll
+      for (int i = 0; i < NE; ++i)
+        if (((i >> 2) * NT + tid) * 4 + (i & 3) == wc) key[i] = INFINITY;
+      idx_out[(size_t)row * k + r] = wc + cfg.col0;
+      picked_p[r] = prow[wc + cfg.col0];
+      local_best(my_key, my_col);
+    } else if (!ok && tid == 0) {
+      idx_out[(size_t)row * k + r] = -1;
+      picked_p[r] = 0.f;
+    }
   }
+  __syncthreads();
   if (tid == 0) {   // conditional probabilities (cnets_llamagen.py:930-938): cumsum in fp64, rounded per prefix
     double acc = 0.0;
     float excl = 0.f;
@@ -92,6 +151,22 @@ __global__ void __launch_bounds__(kDraftThreads) draft_sample_kernel(const Accep
       excl = (float)acc;
     }
   }
+}
+
+template <int DT>
+static int launch_draft(const AcceptParams& P, int k, float* probs, int32_t* idx, float* cond, unsigned rows,
+                        cudaStream_t s) {
+  const int ncols = P.cfg.ncols;
+  if (ncols <= 4 * kDraftGroups * 128) draft_sample_kernel<DT, 128><<<rows, 128, 0, s>>>(P, k, probs, idx, cond);
+  else if (ncols <= 4 * kDraftGroups * 256) draft_sample_kernel<DT, 256><<<rows, 256, 0, s>>>(P, k, probs, idx, cond);
+  else if (ncols <= 4 * kDraftGroups * 512) draft_sample_kernel<DT, 512><<<rows, 512, 0, s>>>(P, k, probs, idx, cond);
+  else if (ncols <= 4 * kDraftGroups * 1024) draft_sample_kernel<DT, 1024><<<rows, 1024, 0, s>>>(P, k, probs, idx, cond);
+  else {
+    set_error("lantern_draft_sample: ncols=%d exceeds %d", ncols, 4 * kDraftGroups * 1024);
+    return LANTERN_E_UNSUPPORTED;
+  }
+  LANTERN_CUDA(cudaGetLastError());
+  return LANTERN_OK;
 }
 
 }  // namespace lantern
@@ -115,10 +190,9 @@ extern "C" LANTERN_API int lantern_draft_sample(const lantern_accept_cfg* cfg, c
   const unsigned rows = (unsigned)(cfg->n_items * cfg->n_rows);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   switch (cfg->logits_dtype) {
-    case LANTERN_F32: draft_sample_kernel<LANTERN_F32><<<rows, kDraftThreads, 0, s>>>(P, k, probs_dev, idx_dev, cond_probs_dev); break;
-    case LANTERN_BF16: draft_sample_kernel<LANTERN_BF16><<<rows, kDraftThreads, 0, s>>>(P, k, probs_dev, idx_dev, cond_probs_dev); break;
-    default: draft_sample_kernel<LANTERN_F16><<<rows, kDraftThreads, 0, s>>>(P, k, probs_dev, idx_dev, cond_probs_dev); break;
+    case LANTERN_F32: return launch_draft<LANTERN_F32>(P, k, probs_dev, idx_dev, cond_probs_dev, rows, s);
+    case LANTERN_BF16: return launch_draft<LANTERN_BF16>(P, k, probs_dev, idx_dev, cond_probs_dev, rows, s);
+    default: return launch_draft<LANTERN_F16>(P, k, probs_dev, idx_dev, cond_probs_dev, rows, s);
   }
-  LANTERN_CUDA(cudaGetLastError());
-  return LANTERN_OK;
 }
+

@@ -11,13 +11,15 @@ constexpr int kKvThreads = 128;
 constexpr int kKvMaxPerThread = 16;
 
 __global__ void __launch_bounds__(kKvThreads) kv_compact_kernel(const lantern_kv_cfg cfg, void* const* slabs,
-                                                                const int32_t* __restrict__ select,
+                                                                const void* __restrict__ select_raw,
                                                                 const int32_t* __restrict__ prev_len,
                                                                 const int32_t* __restrict__ n_keep) {
   const int64_t outer = blockIdx.x;
-  char* slab = static_cast<char*>(slabs[blockIdx.y]);
+  char* slab = static_cast<char*>(slabs ? slabs[blockIdx.y] : cfg.slab0);
   const int b = (int)((outer / cfg.outer_per_batch) % cfg.n_batch);
-  const int keep = n_keep[b], prev = prev_len[b];
+  const int keep = n_keep ? n_keep[b] : cfg.n_keep0, prev = prev_len ? prev_len[b] : cfg.prev_len0;
+  const int32_t* select = static_cast<const int32_t*>(select_raw);
+  const int64_t* select64 = static_cast<const int64_t*>(select_raw);
   const int row_bytes = cfg.head_dim * cfg.elem_bytes;
   const int vpr = row_bytes / 16;   // 16-byte vectors per position
   const int work = keep * vpr;
@@ -26,7 +28,7 @@ __global__ void __launch_bounds__(kKvThreads) kv_compact_kernel(const lantern_kv
   int n = 0;
   for (int w = threadIdx.x; w < work && n < kKvMaxPerThread; w += kKvThreads, ++n) {
     const int i = w / vpr, v = w % vpr;
-    const int src = select[b * cfg.max_keep + i];
+    const int src = cfg.select_i64 ? (int)select64[b * cfg.max_keep + i] : select[b * cfg.max_keep + i];
     regs[n] = *reinterpret_cast<const uint4*>(base + (int64_t)src * row_bytes + v * 16);
   }
   __syncthreads();
@@ -39,11 +41,15 @@ __global__ void __launch_bounds__(kKvThreads) kv_compact_kernel(const lantern_kv
 
 }  // namespace lantern
 
-extern "C" int lantern_kv_compact(const lantern_kv_cfg* cfg, void* const* slab_ptrs_dev, const int32_t* select_dev,
+extern "C" int lantern_kv_compact(const lantern_kv_cfg* cfg, void* const* slab_ptrs_dev, const void* select_dev,
                                   const int32_t* prev_len_dev, const int32_t* n_keep_dev, void* stream) {
   using namespace lantern;
-  if (!cfg || !slab_ptrs_dev || !select_dev || !prev_len_dev || !n_keep_dev) {
-    set_error("lantern_kv_compact: null argument");
+  if (!cfg || !select_dev || (!slab_ptrs_dev && (!cfg->slab0 || cfg->n_slabs != 1))) {
+    set_error("lantern_kv_compact: null argument (slab_ptrs_dev may be NULL only with n_slabs == 1 and cfg.slab0 set)");
+    return LANTERN_E_INVALID;
+  }
+  if (!n_keep_dev && (cfg->n_keep0 < 0 || cfg->n_keep0 > cfg->max_keep)) {
+    set_error("lantern_kv_compact: n_keep0 outside [0, max_keep]");
     return LANTERN_E_INVALID;
   }
   const int row_bytes = cfg->head_dim * cfg->elem_bytes;

@@ -327,17 +327,19 @@ def kv_compact(past_key_values_data_list: Sequence[torch.Tensor], select_indices
     n = int(select_indices.numel())
     for data in past_key_values_data_list:
         dev = data.device
-        sel = select_indices.to(device=dev, dtype=torch.int32).contiguous().view(1, n)
+        sel = select_indices
+        if sel.device != dev or sel.dtype not in (torch.int64, torch.int32) or not sel.is_contiguous():
+            sel = sel.to(device=dev, dtype=torch.int64).contiguous()
         cfg = _abi.KvCfg()
         cfg.n_slabs, cfg.elem_bytes = 1, data.element_size()
         cfg.n_outer = data.shape[0] * data.shape[1] * data.shape[2]
         cfg.outer_per_batch, cfg.n_batch = 1, 1          # one prompt: every outer slice uses select row 0
         cfg.s_max, cfg.head_dim, cfg.max_keep = data.shape[3], data.shape[4], n
-        ptrs = torch.tensor([data.data_ptr()], dtype=torch.int64, device=dev)
-        prev = torch.tensor([prev_len], dtype=torch.int32, device=dev)
-        keep = torch.tensor([n], dtype=torch.int32, device=dev)
-        _abi.check(lib.lantern_kv_compact(C.byref(cfg), ptrs.data_ptr(), sel.data_ptr(), prev.data_ptr(),
-                                          keep.data_ptr(), torch.cuda.current_stream(dev).cuda_stream))
+        # batch-1 call: slab pointer and lengths travel by value, the index tensor is used as it is (no H2D copy)
+        cfg.slab0, cfg.prev_len0, cfg.n_keep0 = data.data_ptr(), int(prev_len), n
+        cfg.select_i64 = int(sel.dtype == torch.int64)
+        _abi.check(lib.lantern_kv_compact(C.byref(cfg), None, sel.data_ptr(), None, None,
+                                          torch.cuda.current_stream(dev).cuda_stream))
     return prev_len + n
 
 

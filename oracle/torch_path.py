@@ -174,3 +174,58 @@ def verify_step(cond: torch.Tensor, uncond: Optional[torch.Tensor], cfg_scale: f
                                                   lantern, lantern_k, lantern_delta, table)
     tok = sample_token(sample_p, float(uniforms[draws]))
     return best, a, tok, sample_p, draws + 1
+
+
+# --------------------------------------------------------------------------------------------------------------------
+# Next rows: torch op sequences of the drafter-side helpers, for GPU-PyTorch baseline timing
+# --------------------------------------------------------------------------------------------------------------------
+def dynamic_tree_tail(scores: torch.Tensor, tokens: torch.Tensor, parents: torch.Tensor, sample_token: torch.Tensor,
+                      total_tokens: int, top_k: int, sort_rows: bool = True):
+    """Tail of ``topK_genrate`` (cnets_llamagen.py:831-912) as the reference runs it: device topk / sort /
+    searchsorted, then ``.tolist()`` round trips, a CPU ancestor-mask loop and Python list work for the leaf paths.
+    Inputs are the flattened lists the expansion loop leaves behind.  Returns (draft_tokens [1,T], retrieve_indices
+    [L,D], tree_mask [1,1,T,T], tree_position_ids [T])."""
+    picked = torch.sort(torch.topk(scores, total_tokens, dim=-1).indices).values
+    draft_tokens = torch.cat((sample_token[:1], tokens[picked]), dim=0)
+    draft_parents = parents[picked // top_k].long()
+    mask_index = torch.searchsorted(picked, draft_parents - 1, right=False)
+    mask_index[draft_parents == 0] = -1
+    mask_index = mask_index + 1
+    par = mask_index.tolist()                                   # host sync
+    tree_mask = torch.eye(total_tokens + 1).bool()               # CPU, like the reference
+    tree_mask[:, 0] = True
+    for i in range(total_tokens):
+        tree_mask[i + 1].add_(tree_mask[par[i]])
+    position_ids = torch.sum(tree_mask, dim=1) - 1
+    max_depth = int(torch.max(position_ids).item()) + 1
+    inner = set(torch.unique(mask_index).tolist())              # host sync
+    depth_of = position_ids.tolist()
+    paths = []
+    for node in range(total_tokens + 1):
+        if node in inner:
+            continue
+        row = [-1] * max_depth
+        cur = node
+        for j in range(depth_of[node], -1, -1):
+            row[j] = cur
+            cur = par[cur - 1]
+        paths.append(row)
+    if sort_rows:
+        big = total_tokens + 5
+        paths.sort(key=lambda r: [x if x >= 0 else big for x in r])
+    retrieve = torch.tensor(paths, dtype=torch.long)
+    return draft_tokens[None], retrieve, tree_mask.float()[None, None], position_ids.to(scores.device)
+
+
+def drafter_sample(logits: torch.Tensor, warp: Optional[O.Warp], k: int):
+    """``Model.sample`` (cnets_llamagen.py:924-940): warp, softmax, ``multinomial`` without replacement, gathered
+    probabilities rescaled by the mass still available before each draw."""
+    if warp is not None:
+        logits = hf_warp(logits, warp)
+    probs = torch.softmax(logits, dim=-1)
+    idx = torch.multinomial(probs, k, replacement=False)
+    picked = probs.gather(-1, idx)
+    drawn_before = torch.nn.functional.pad(picked.cumsum(-1)[:, :-1], (1, 0))    # mass removed by the earlier draws
+    cond = picked / (1 - drawn_before)
+    cond = torch.where(torch.isfinite(cond), cond, torch.full_like(cond, -1.0)).clamp(0.0, 1.0)
+    return idx, cond, probs

@@ -173,6 +173,36 @@ def test_bonus_token_and_kv_compact():
         assert np.array_equal(s.float().cpu().numpy(), w)
 
 
+def test_kv_compact_ragged_batch_device_arrays():
+    """the batched form of lantern_kv_compact — several slabs, per-item accepted counts and previous
+    lengths held on the device (no host sync), int32 select rows padded to D."""
+    import ctypes as C
+    from lantern_b200 import _abi
+    dev = torch.device("cuda")
+    lib = _abi.load()
+    layers2, B, H, S, hd, D = 4, 3, 2, 96, 32, 6
+    slabs = [torch.randn(layers2, B, H, S, hd, device=dev, dtype=torch.bfloat16) for _ in range(2)]
+    want = [s.clone().float().cpu().numpy() for s in slabs]
+    prev = np.array([40, 17, 60], dtype=np.int32)
+    keep = np.array([4, 1, 6], dtype=np.int32)
+    sel = np.full((B, D), -1, dtype=np.int32)
+    sel[0, :4] = [40, 43, 47, 52]
+    sel[1, :1] = [17]
+    sel[2, :6] = [61, 62, 64, 70, 71, 79]
+    cfg = _abi.KvCfg()
+    cfg.n_slabs, cfg.elem_bytes, cfg.n_outer = 2, 2, layers2 * B * H
+    cfg.outer_per_batch, cfg.n_batch, cfg.s_max, cfg.head_dim, cfg.max_keep = H, B, S, hd, D
+    ptrs = torch.tensor([s.data_ptr() for s in slabs], dtype=torch.int64, device=dev)
+    d_sel, d_prev, d_keep = (torch.from_numpy(a).to(dev) for a in (sel, prev, keep))
+    _abi.check(lib.lantern_kv_compact(C.byref(cfg), ptrs.data_ptr(), d_sel.data_ptr(), d_prev.data_ptr(),
+                                      d_keep.data_ptr(), torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    for s, w in zip(slabs, want):
+        for b in range(B):
+            O.kv_compact(w[:, b], sel[b, :keep[b]], int(prev[b]))
+        assert np.array_equal(s.float().cpu().numpy(), w)
+
+
 def test_greedy_branch():
     logits = torch.randn(6, 5, 128, device="cuda")
     cand = torch.randint(0, 128, (6, 5), device="cuda")

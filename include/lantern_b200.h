@@ -58,7 +58,8 @@ enum { LANTERN_ROW_IMAGE = 0, LANTERN_ROW_NEWLINE = 1, LANTERN_ROW_EOI = 2 };
 /* Bits of lantern_accept_out.flags[b]. */
 enum {
   LANTERN_OUT_RESIDUAL_TAIL = 1,    /* sample_p is the residual distribution (adjustflag path) */
-  LANTERN_OUT_UNIFORM_FALLBACK = 2  /* a residual summed to 0 and was reset to ones (:775-776) */
+  LANTERN_OUT_UNIFORM_FALLBACK = 2, /* a residual summed to 0 and was reset to ones (:775-776) */
+  LANTERN_OUT_ROWS_READ_SHIFT = 8   /* bits 8..15: logits rows the walk turned into probabilities for this item */
 };
 
 #define LANTERN_MAX_SYNTAX_TOKENS 8
@@ -259,9 +260,14 @@ LANTERN_API void lantern_philox_uniforms(uint64_t seed, uint64_t step, uint32_t 
 
 /*
  * Host-buffer session: the call a reference-side caller makes when its logits live in host
- * memory.  Owns device buffers, pinned staging and a stream sized for `cfg`; `lantern_session_step`
- * copies only the live column window of the logits to the device, runs lantern_accept_fused and
- * copies the per-item results back, synchronously.
+ * memory.  Owns device buffers, pinned staging and a stream sized for `cfg`; `lantern_session_step` is synchronous.
+ * Two routes, same results:
+ *   - in place: if the logits are page-locked host memory the device can address (cudaHostAlloc /
+ *     cudaHostRegister, e.g. a torch pin_memory() tensor) and the window is lazy-eligible (see
+ *     lantern_accept_phases), the walk reads the rows it visits straight from host memory over PCIe: only
+ *     ~accept_length + 2 of the T tree rows of each prompt cross the bus (flags bits 8..15 report how many);
+ *   - staged: otherwise (pageable memory, top-p, other window widths, or LANTERN_SESSION_STAGED=1 in the
+ *     environment) the live column window of every row is copied to the device and lantern_accept_fused runs on it.
  */
 typedef struct lantern_session lantern_session;
 LANTERN_API int lantern_session_create(const lantern_accept_cfg* cfg, const int32_t* nbr_table_host, int32_t table_rows,
@@ -269,6 +275,8 @@ LANTERN_API int lantern_session_create(const lantern_accept_cfg* cfg, const int3
 LANTERN_API int lantern_session_step(lantern_session* s, const lantern_accept_cfg* cfg, const lantern_accept_in* in_host,
                          const lantern_accept_out* out_host);
 LANTERN_API void lantern_session_destroy(lantern_session* s);
+/* Route of the last lantern_session_step: 1 = logits read in place from page-locked host memory, 0 = staged. */
+LANTERN_API int lantern_session_last_route(const lantern_session* s);
 
 #ifdef __cplusplus
 }

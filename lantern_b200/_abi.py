@@ -22,7 +22,7 @@ EXPORTS = (
     "lantern_accept_phases",
     "lantern_sample_tokens", "lantern_kv_compact", "lantern_build_neighbors", "lantern_philox_uniforms",
     "lantern_session_create", "lantern_session_step", "lantern_session_destroy", "lantern_debug_dist_gemm", "lantern_debug_neighbors_path", "lantern_build_dynamic_tree", "lantern_draft_sample",
-    "lantern_tree_from_candidates",
+    "lantern_tree_from_candidates", "lantern_session_last_route",
 )
 
 
@@ -122,6 +122,8 @@ def load() -> C.CDLL:
     lib.lantern_session_create.argtypes = [C.POINTER(AcceptCfg), C.c_void_p, C.c_int32, C.POINTER(C.c_void_p)]
     lib.lantern_session_step.restype = C.c_int
     lib.lantern_session_step.argtypes = [C.c_void_p, C.POINTER(AcceptCfg), C.POINTER(AcceptIn), C.POINTER(AcceptOut)]
+    lib.lantern_session_last_route.restype = C.c_int
+    lib.lantern_session_last_route.argtypes = [C.c_void_p]
     lib.lantern_session_destroy.restype = None
     lib.lantern_session_destroy.argtypes = [C.c_void_p]
     _lib = lib

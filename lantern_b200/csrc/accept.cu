@@ -428,6 +428,7 @@ __global__ void __launch_bounds__(kWalkThreads) walk_kernel(const AcceptParams P
     if (tkn == extra_tok) return p_extra;
     return p_out;
   };
+  int rows_read = 0;   // logits rows materialised into S.p (reported in the flags word; one-hot rows read nothing)
   auto set_distribution = [&](int node, bool raw) {
     const long long row = (long long)b * T + node;
     RowStats st;
@@ -448,8 +449,10 @@ __global__ void __launch_bounds__(kWalkThreads) walk_kernel(const AcceptParams P
         extra_tok = -1; p_extra = 0.f;
       }
     } else if (LNE > 0) {
+      ++rows_read;
       lazy_probs<DT, (LNE > 0 ? LNE : 4)>(P, b, node, raw, S.p, lazy_park, lazy_sm, lazy_part, z_run, win_run);
     } else {
+      ++rows_read;
       if (raw) st = raw_row_stats<DT, VEC>(P, b, node, S.fscr, S.dscr);
       load_probs<DT, VEC>(P, b, node, st, S.p, raw);
     }
@@ -720,7 +723,7 @@ __global__ void __launch_bounds__(kWalkThreads) walk_kernel(const AcceptParams P
     P.out.best_candidate[b] = best;
     P.out.token[b] = token;
     if (P.out.n_draws) P.out.n_draws[b] = draws;
-    if (P.out.flags) P.out.flags[b] = out_flags;
+    if (P.out.flags) P.out.flags[b] = out_flags | (min(rows_read, 255) << LANTERN_OUT_ROWS_READ_SHIFT);
   }
   for (int i = tid; i < D; i += NT) {
     if (P.out.path_tokens) P.out.path_tokens[(size_t)b * D + i] = i <= a ? cand(best, i) : -1;

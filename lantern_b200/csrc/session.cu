@@ -27,6 +27,7 @@ struct lantern_session {
   float* d_sample_p = nullptr;
   void* d_work = nullptr;
   size_t work_bytes = 0;
+  int last_in_place = 0;       // route of the last step (lantern_session_last_route)
 };
 
 namespace lantern {
@@ -107,6 +108,9 @@ extern "C" int lantern_session_create(const lantern_accept_cfg* cfg, const int32
   return LANTERN_OK;
 }
 
+// 1 if the last step read the logits in place from page-locked host memory, 0 if it staged them on the device.
+extern "C" int lantern_session_last_route(const lantern_session* s) { return s ? s->last_in_place : -1; }
+
 extern "C" int lantern_session_step(lantern_session* s, const lantern_accept_cfg* cfg, const lantern_accept_in* in,
                                     const lantern_accept_out* out) {
   if (!s || !cfg || !in || !out) {
@@ -143,8 +147,24 @@ extern "C" int lantern_session_step(lantern_session* s, const lantern_accept_cfg
     }
     return cudaSuccess;
   };
-  LANTERN_CUDA(copy_rows(s->d_cond, in->logits_cond));
-  if (in->logits_uncond) LANTERN_CUDA(copy_rows(s->d_uncond, in->logits_uncond));
+  // In-place route: page-locked logits the device can address are read by the lazy walk directly (zero-copy).
+  const void *dev_cond = nullptr, *dev_uncond = nullptr;
+  bool in_place = getenv("LANTERN_SESSION_STAGED") == nullptr;
+  if (in_place) {
+    auto mapped = [](const void* host, const void** dev) -> bool {
+      cudaPointerAttributes a;
+      if (cudaPointerGetAttributes(&a, host) != cudaSuccess) { cudaGetLastError(); return false; }
+      if (a.type != cudaMemoryTypeHost || !a.devicePointer) return false;
+      *dev = a.devicePointer;
+      return true;
+    };
+    in_place = mapped(in->logits_cond, &dev_cond) && (!in->logits_uncond || mapped(in->logits_uncond, &dev_uncond));
+  }
+  s->last_in_place = 0;
+  if (!in_place) {
+    LANTERN_CUDA(copy_rows(s->d_cond, in->logits_cond));
+    if (in->logits_uncond) LANTERN_CUDA(copy_rows(s->d_uncond, in->logits_uncond));
+  }
   LANTERN_CUDA(cudaMemcpyAsync(s->d_tokens, in->tree_tokens, rows * 4, cudaMemcpyHostToDevice, st));
   const size_t n_ri = (size_t)(cfg->retrieve_shared ? 1 : B) * L * D;
   LANTERN_CUDA(cudaMemcpyAsync(s->d_retrieve, in->retrieve, n_ri * 4, cudaMemcpyHostToDevice, st));
@@ -213,7 +233,20 @@ extern "C" int lantern_session_step(lantern_session* s, const lantern_accept_cfg
     if (!s->d_sample_p) LANTERN_CUDA(cudaMalloc(&s->d_sample_p, (size_t)m.n_items * m.vocab * 4));
     dout.sample_p = s->d_sample_p;
   }
-  int rc = lantern_accept_fused(&dc, &di, &dout, s->d_work, s->work_bytes, st);
+  int rc = LANTERN_E_UNSUPPORTED;
+  if (in_place) {
+    lantern_accept_cfg hc = *cfg;           // host strides, absolute columns
+    lantern_accept_in hi = di;
+    hi.logits_cond = dev_cond;
+    hi.logits_uncond = in->logits_uncond ? dev_uncond : nullptr;
+    rc = lantern_accept_phases(&hc, &hi, &dout, s->d_work, s->work_bytes, st, 6);
+    if (rc == LANTERN_OK) s->last_in_place = 1;
+    else if (rc == LANTERN_E_UNSUPPORTED) {   // not lazy-eligible: stage the window after all
+      LANTERN_CUDA(copy_rows(s->d_cond, in->logits_cond));
+      if (in->logits_uncond) LANTERN_CUDA(copy_rows(s->d_uncond, in->logits_uncond));
+    }
+  }
+  if (rc == LANTERN_E_UNSUPPORTED) rc = lantern_accept_fused(&dc, &di, &dout, s->d_work, s->work_bytes, st);
   if (rc) return rc;
   const size_t n_out = (size_t)B * (5 + 2 * (size_t)D);
   LANTERN_CUDA(cudaMemcpyAsync(s->h_out, s->d_out, n_out * 4, cudaMemcpyDeviceToHost, st));

@@ -255,6 +255,7 @@ def run_b200(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=dev)
 
     fam = verify.FAMILIES[args.family]
@@ -490,12 +491,11 @@ def torch_gpu_baseline(args, fam, bt, ours, table_np, k, tpi):
 
 
 def run_e2e(args, fam, ver, table_np, tree_pool, rank, dev, world):
-    """Host-buffer path: pinned host logits -> lantern_session_step (H2D window copy + kernels + D2H results)."""
-    import ctypes as C
+    """Host-buffer path through the public API (lantern_b200.session.HostSession -> lantern_session_step): pinned host
+    logits in, host results out, synchronous."""
     import torch
-    from lantern_b200 import _abi
-    lib = _abi.load()
-    B, T, V = args.items, args.total_tokens, fam.vocab
+    from lantern_b200.session import HostSession
+    B, T = args.items, args.total_tokens
     dt = torch.float32 if args.logits_dtype == "fp32" else torch.bfloat16
     trees = [tree_pool[i % len(tree_pool)] for i in range(B)]
     hb = device_batch(args, fam, trees, 777 + rank, dev)
@@ -510,22 +510,13 @@ def run_e2e(args, fam, ver, table_np, tree_pool, rank, dev, world):
     L, D = retrieve.shape[1:]
     del hb
     torch.cuda.synchronize()
-    cfg = ver._cfg(B, T, L, D, host["cond"], False, T + 1, (0, 0))
-    sess = C.c_void_p()
-    _abi.check(lib.lantern_session_create(C.byref(cfg), table_np.ctypes.data, table_np.shape[0], C.byref(sess)))
-    ain = _abi.AcceptIn()
-    ain.logits_cond, ain.logits_uncond = host["cond"].data_ptr(), host["uncond"].data_ptr()
-    ain.tree_tokens, ain.retrieve, ain.uniforms = tokens.data_ptr(), retrieve.data_ptr(), uni.data_ptr()
-    out_np = {n: np.zeros(B, dtype=np.int32) for n in ("accept_length", "best_candidate", "token", "n_draws", "flags")}
-    path = np.zeros((B, D), dtype=np.int32)
-    sel = np.zeros((B, D), dtype=np.int32)
-    aout = _abi.AcceptOut()
-    aout.accept_length, aout.best_candidate = out_np["accept_length"].ctypes.data, out_np["best_candidate"].ctypes.data
-    aout.token, aout.n_draws, aout.flags = out_np["token"].ctypes.data, out_np["n_draws"].ctypes.data, out_np["flags"].ctypes.data
-    aout.path_tokens, aout.select_indices = path.ctypes.data, sel.ctypes.data
+    sess = HostSession(ver, B, T, L, D, logits_dtype=dt, n_uniforms=T + 1)
+
+    def step():
+        return sess.step(host["cond"], host["uncond"], tokens, retrieve, uniforms=uni)
     steps = max(3, min(args.steps, 10))
     for _ in range(2):
-        _abi.check(lib.lantern_session_step(sess, C.byref(cfg), C.byref(ain), C.byref(aout)))
+        step()
     torch.cuda.synchronize()
     if world > 1:
         import torch.distributed as dist
@@ -533,17 +524,17 @@ def run_e2e(args, fam, ver, table_np, tree_pool, rank, dev, world):
     # the rows the in-place route reads fit in L2 many times over, so L2 is flushed (256 MB memset, outside the
     # timed region) before every step; each step is timed on its own, host clock around the synchronous call
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-    tok, rows_read, ms = 0, 0, 0.0
+    tok, rows_read, ms, in_place = 0, 0, 0.0, False
     for _ in range(steps):
         flush.zero_()
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        _abi.check(lib.lantern_session_step(sess, C.byref(cfg), C.byref(ain), C.byref(aout)))   # synchronous
+        r = step()
         ms += (time.perf_counter() - t0) * 1e3
-        tok += int(out_np["accept_length"].sum()) + B
-        rows_read += int(((out_np["flags"] >> 8) & 0xFF).sum())
-    in_place = int(lib.lantern_session_last_route(sess)) == 1
-    lib.lantern_session_destroy(sess)
+        tok += int(r.accept_length.sum()) + B
+        rows_read += int(r.rows_read.sum())
+        in_place = r.in_place
+    sess.close()
     eb = 4 if args.logits_dtype == "fp32" else 2
     small = tokens.numel() * 4 + retrieve.numel() * 4 + uni.numel() * 4
     if in_place:     # the walk read the visited rows (cond + uncond windows) straight from pinned host memory

@@ -123,6 +123,43 @@ def test_accept_sweep_shapes(B, T):
         R.compare(res, i, o)
 
 
+def test_host_session_python_api():
+    """lantern_b200.session.HostSession: pinned torch tensors (in place) and numpy arrays (staged) give the oracle's
+    results; the in-place route reads no more than accept_length + 2 rows per prompt."""
+    from lantern_b200.session import HostSession
+    built, orcs, seed = [], [], 12500
+    while len(built) < 4:
+        b = CG.build(dict(family="lumina_mgpt", seed=seed, depth=5))
+        seed += 1
+        o = CG.oracle_step(b)
+        if o.margin >= 1e-5:
+            built.append(b)
+            orcs.append(o)
+    b0 = built[0]
+    fam = R.family_spec(b0)
+    p = b0.params
+    k = min(int(p["lantern_k"]), b0.fam.ncols - 1)
+    ver = verify.Verifier(fam, temperature=p["temperature"], top_k=p["top_k"], cfg_scale=p["cfg_scale"], lantern=True,
+                          lantern_k=k, lantern_delta=p["lantern_delta"],
+                          nbr_table=torch.from_numpy(b0.table.astype(np.int32)).cuda())
+    cond = np.ascontiguousarray(np.stack([c.cond for c in built]))
+    uncond = np.ascontiguousarray(np.stack([c.uncond for c in built]))
+    tokens = np.ascontiguousarray(np.stack([c.tree.tokens for c in built]).astype(np.int32))
+    ri = R.pad_retrieve([c.tree.retrieve_indices for c in built])
+    uni = np.ascontiguousarray(np.stack([c.uniforms for c in built]).astype(np.float32))
+    with HostSession(ver, len(built), b0.tree.T, ri.shape[1], ri.shape[2], n_uniforms=uni.shape[1]) as sess:
+        staged = sess.step(cond, uncond, tokens, ri, uniforms=uni, want_sample_p=True)
+        pinned = sess.step(torch.from_numpy(cond).pin_memory(), torch.from_numpy(uncond).pin_memory(), tokens, ri,
+                           uniforms=uni, want_sample_p=True)
+    assert not staged.in_place and pinned.in_place
+    for r in (staged, pinned):
+        for i, o in enumerate(orcs):
+            assert int(r.accept_length[i]) == o.accept_length and int(r.token[i]) == o.token
+            assert int(r.best_candidate[i]) == o.best_candidate and int(r.n_draws[i]) == o.n_uniforms
+            R.assert_probs_close(r.sample_p[i], o.sample_p)
+    assert np.all(pinned.rows_read <= pinned.accept_length + 2) and np.all(pinned.rows_read >= 1)
+
+
 @pytest.mark.parametrize("N,d", [(512, 8), (1000, 8), (1024, 256), (2048, 40)])
 def test_tensor_core_distance_gemm_within_bound(N, d):
     """tcgen05 TF32 distance GEMM against fp64 distances: inside the error bound the exact re-rank relies on."""

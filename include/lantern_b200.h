@@ -163,6 +163,22 @@ LANTERN_API int lantern_accept_phases(const lantern_accept_cfg* cfg, const lante
                                       void* stream, int phases);
 
 /*
+ * Greedy verification (logits_processor is None / temperature 0), tree form, LlamaGen / Anole / vanilla families:
+ * drafters/utils.py:356-369 and ea_model_anole.py:789-902.  cfg->lantern = 0: a child is accepted iff its token is the
+ * argmax of its parent's (CFG-mixed, masked) logits row.  cfg->lantern = 1: the "TVD" relaxation of the reference -
+ * gtp = softmax(row), px = gtp[x], approx = px + cumsum(gtp[neighbours]), tvd = 0.5|px - approx| + cumsum(0.5 gtp[nb]),
+ * last position within lantern_delta (or (delta-1) px) replaces gtp[x]; accepted iff x is then the row's argmax.
+ * accept_length = longest accepted prefix over the leaf paths (first path on ties, path 0 if none).  out->token is
+ * the argmax of the last accepted node's row, which is also written to out->sample_p ([B, vocab], the reference's
+ * third return value `logits[best, accept_length]`) when that pointer is set.  Rows must span the vocabulary
+ * (row_stride >= vocab); warp knobs, uniforms and the static-tree inputs are ignored.  Workspace: 4 bytes per tree row.
+ */
+LANTERN_API size_t lantern_accept_greedy_workspace_bytes(const lantern_accept_cfg* cfg);
+LANTERN_API int lantern_accept_greedy(const lantern_accept_cfg* cfg, const lantern_accept_in* in,
+                                      const lantern_accept_out* out, void* workspace_dev, size_t workspace_bytes,
+                                      void* stream);
+
+/*
  * Glue for the reference's evaluate_posterior signature (drafters/utils.py:333, ea_model_llamagen.py:709), which
  * receives `candidates [L, D]` (int64, -1 padded; token of node retrieve_indices[j, i]) instead of the tree's token
  * vector: writes tree_tokens [n_rows] int32 (0 for unreachable nodes) and the int32 copy of retrieve_indices

@@ -22,7 +22,8 @@ EXPORTS = (
     "lantern_accept_phases",
     "lantern_sample_tokens", "lantern_kv_compact", "lantern_build_neighbors", "lantern_philox_uniforms",
     "lantern_session_create", "lantern_session_step", "lantern_session_destroy", "lantern_debug_dist_gemm", "lantern_debug_neighbors_path", "lantern_build_dynamic_tree", "lantern_draft_sample",
-    "lantern_tree_from_candidates", "lantern_session_last_route",
+    "lantern_tree_from_candidates", "lantern_session_last_route", "lantern_accept_greedy",
+    "lantern_accept_greedy_workspace_bytes",
 )
 
 
@@ -98,6 +99,10 @@ def load() -> C.CDLL:
                                          C.c_void_p, C.c_size_t, C.c_void_p]
     lib.lantern_accept_phases.restype = C.c_int
     lib.lantern_accept_phases.argtypes = lib.lantern_accept_fused.argtypes + [C.c_int]
+    lib.lantern_accept_greedy_workspace_bytes.restype = C.c_size_t
+    lib.lantern_accept_greedy_workspace_bytes.argtypes = [C.POINTER(AcceptCfg)]
+    lib.lantern_accept_greedy.restype = C.c_int
+    lib.lantern_accept_greedy.argtypes = lib.lantern_accept_fused.argtypes
     lib.lantern_sample_tokens.restype = C.c_int
     lib.lantern_sample_tokens.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
                                           C.c_void_p]

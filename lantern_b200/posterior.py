@@ -201,15 +201,13 @@ def _io(device) -> _HostIO:
     return io
 
 
-def _verify(fam: FamilySpec, logits, candidates: torch.Tensor, *, temp=1.0, top_p=1.0, top_k=0, lantern=False,
-            lantern_k=1000, lantern_delta=0.1, nearest_latents=None, static_inputs=None, rng="python",
-            philox=(0, 0), want_sample_p=True):
-    """Returns (best_candidate 0-d int64 CPU tensor, accept_length int, sample_p [V] with ``_lantern_token``)."""
+def _tree_inputs(logits, candidates: torch.Tensor, stream):
+    """Kernel-side form of what the reference hands to evaluate_posterior: (cond [1,T,V], uncond, cfg_scale,
+    tree_tokens [1,T] int32, retrieve [1,L,D] int32, row_kinds, T, Lumina top-k)."""
     fused = isinstance(logits, TreeLogits)
     device = logits.device
     cand = candidates if candidates.device == device else candidates.to(device)
     L, D = cand.shape
-    stream = torch.cuda.current_stream(device)
     if fused:
         cond, uncond, cfg_scale = logits.cond, logits.uncond, logits.cfg_scale
         ri64 = logits.retrieve_indices
@@ -222,20 +220,47 @@ def _verify(fam: FamilySpec, logits, candidates: torch.Tensor, *, temp=1.0, top_
         tokens, retrieve = ibuf[:T].view(1, T), ibuf[T:].view(1, L, D)
         _abi.check(_abi.load().lantern_tree_from_candidates(cand.data_ptr(), ri64.data_ptr(), L, D, T,
                                                             tokens.data_ptr(), retrieve.data_ptr(), stream.cuda_stream))
-        kinds = logits.row_kinds
-        if fam.family_id == _abi.FAMILY_LUMINA:
-            top_k = logits.top_k
-    else:
-        V = logits.shape[-1]
-        cond, uncond, cfg_scale = logits.reshape(1, L * D, V), None, 1.0
-        if cond.stride(2) != 1:
-            cond = cond.contiguous()
-        T = L * D
-        tokens = cand.reshape(-1).to(torch.int32)
-        ids = torch.arange(T, device=device, dtype=torch.int32).view(L, D)
-        retrieve = torch.where(cand >= 0, ids, torch.full_like(ids, -1)).contiguous()[None]
-        tokens = torch.where(tokens >= 0, tokens, torch.zeros_like(tokens)).view(1, T).contiguous()
-        kinds = None
+        return cond, uncond, cfg_scale, tokens, retrieve, logits.row_kinds, T, logits.top_k
+    V = logits.shape[-1]
+    cond = logits.reshape(1, L * D, V)
+    if cond.stride(2) != 1:
+        cond = cond.contiguous()
+    T = L * D
+    tokens = cand.reshape(-1).to(torch.int32)
+    ids = torch.arange(T, device=device, dtype=torch.int32).view(L, D)
+    retrieve = torch.where(cand >= 0, ids, torch.full_like(ids, -1)).contiguous()[None]
+    tokens = torch.where(tokens >= 0, tokens, torch.zeros_like(tokens)).view(1, T).contiguous()
+    return cond, None, 1.0, tokens, retrieve, None, T, None
+
+
+def _verify_greedy(fam: FamilySpec, logits, candidates: torch.Tensor, lantern=False, lantern_k=1000, lantern_delta=0.1,
+                   nearest_latents=None):
+    """Greedy branches (``logits_processor is None``): drafters/utils.py:356-369, ea_model_anole.py:789-902.  Returns the
+    reference's greedy triple: (best_candidate 0-d int64 on the device, accept_length 0-d int64 on the device,
+    logits[best, accept_length] [V])."""
+    device = logits.device
+    stream = torch.cuda.current_stream(device)
+    cond, uncond, cfg_scale, tokens, retrieve, _, _, _ = _tree_inputs(logits, candidates, stream)
+    table, k = None, int(lantern_k)
+    if lantern:
+        k = min(k, fam.ncols - 1)
+        table = device_table(nearest_latents, device, min(k + 1, fam.ncols - 1))
+    ver = _get_verifier(fam, 1.0, 1.0, 0, cfg_scale, lantern, k, lantern_delta, table, None, device)
+    res = ver.greedy(cond, uncond, tokens, retrieve)
+    row = res.sample_p[0]
+    row._lantern_argmax = res.token[0]     # device scalar: sample_bonus_token(do_sample=False) reuses it
+    return res.best_candidate[0].long(), res.accept_length[0].long(), row
+
+
+def _verify(fam: FamilySpec, logits, candidates: torch.Tensor, *, temp=1.0, top_p=1.0, top_k=0, lantern=False,
+            lantern_k=1000, lantern_delta=0.1, nearest_latents=None, static_inputs=None, rng="python",
+            philox=(0, 0), want_sample_p=True):
+    """Returns (best_candidate 0-d int64 CPU tensor, accept_length int, sample_p [V] with ``_lantern_token``)."""
+    device = logits.device
+    stream = torch.cuda.current_stream(device)
+    cond, uncond, cfg_scale, tokens, retrieve, kinds, T, lumina_top_k = _tree_inputs(logits, candidates, stream)
+    if fam.family_id == _abi.FAMILY_LUMINA and lumina_top_k is not None:
+        top_k = lumina_top_k
     table, k = None, int(lantern_k)
     if lantern:
         n_codes = fam.ncols
@@ -280,6 +305,8 @@ def _verify(fam: FamilySpec, logits, candidates: torch.Tensor, *, temp=1.0, top_
 def evaluate_posterior(logits, candidates, logits_processor, rng: str = "python"):
     """drafters/utils.py:333-410."""
     if logits_processor is None or len(logits_processor) == 0 and not getattr(logits_processor, "temperature", 1) > 1e-5:
+        if isinstance(logits, TreeLogits):
+            return _verify_greedy(verify.vanilla(logits.shape[-1]), logits, candidates)
         return evaluate_posterior_greedy(logits, candidates)
     t, p, k = _warp_knobs(logits_processor)
     fam = verify.vanilla(logits.shape[-1])
@@ -312,7 +339,8 @@ def sample_bonus_token(sample_p: torch.Tensor, do_sample: bool = True) -> torch.
     ``[1, 1]`` int64.  Reuses the token the fused step already drew when ``sample_p`` came from it."""
     tok = getattr(sample_p, "_lantern_token", None)
     if not do_sample:
-        return torch.argmax(sample_p)[None, None]
+        am = getattr(sample_p, "_lantern_argmax", None)
+        return (torch.argmax(sample_p) if am is None else am.long())[None, None]
     if tok is None:
         u = torch.rand(1)
         tok = int(verify.sample_tokens(sample_p.float().view(1, -1), u)[0])
@@ -469,8 +497,11 @@ class VerifyMixin:
                            lantern_delta=0.1):
         """ea_model_llamagen.py:709-787 / ea_model_anole.py:709-788 (sampling branch)."""
         if logits_processor is None:
-            if lantern:
-                raise NotImplementedError("greedy + LANTERN (ea_model_llamagen.py:789-905) is not on the BASELINE path")
+            # greedy branches (ea_model_anole.py:789-902); gathered logits without relaxation stay index arithmetic
+            if lantern or isinstance(logits, TreeLogits):
+                return _verify_greedy(self._family(logits.shape[-1]), logits, candidates, lantern=lantern,
+                                      lantern_k=lantern_k, lantern_delta=lantern_delta,
+                                      nearest_latents=getattr(self, "nearest_latents", None))
             return evaluate_posterior_greedy(logits, candidates)
         t, p, k = _warp_knobs(logits_processor)
         fam = self._family(logits.shape[-1])

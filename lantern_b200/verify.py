@@ -228,6 +228,51 @@ class Verifier:
         return res
 
 
+def _greedy(self, logits_cond: torch.Tensor, logits_uncond: Optional[torch.Tensor], tree_tokens: torch.Tensor,
+            retrieve: torch.Tensor, want_row: bool = True) -> VerifyResult:
+    """Greedy verification (temperature 0): ``lantern_accept_greedy``.  Same tensor layout as ``step``; the warp
+    knobs are ignored, ``lantern`` selects the relaxed variant.  ``sample_p`` of the result is the CFG-mixed logits row
+    of the last accepted node (the reference's third return value) and ``token`` its argmax."""
+    if logits_cond.dim() != 3 or logits_cond.stride(2) != 1:
+        raise ValueError("logits must be [B, T, V] with a contiguous last dimension")
+    if logits_uncond is not None and (logits_uncond.shape != logits_cond.shape
+                                      or logits_uncond.stride() != logits_cond.stride()
+                                      or logits_uncond.dtype != logits_cond.dtype):
+        raise ValueError("logits_uncond must match logits_cond in shape, strides and dtype")
+    B, T, V = logits_cond.shape
+    shared = retrieve.dim() == 2
+    L, D = retrieve.shape[-2:]
+    for name, t in (("tree_tokens", tree_tokens), ("retrieve", retrieve)):
+        if t.dtype != torch.int32 or not t.is_contiguous() or not t.is_cuda:
+            raise ValueError(f"{name} must be a contiguous int32 CUDA tensor")
+    cfg = self._cfg(B, T, L, D, logits_cond, shared, 0, (0, 0))
+    ain = _abi.AcceptIn()
+    ain.logits_cond, ain.logits_uncond = _ptr(logits_cond), _ptr(logits_uncond)
+    ain.tree_tokens, ain.retrieve = _ptr(tree_tokens), _ptr(retrieve)
+    ain.nbr_table = _ptr(self.nbr_table)
+    dev = logits_cond.device
+    ints = torch.empty(B * (5 + 2 * D), dtype=torch.int32, device=dev)
+    res = VerifyResult(ints[0:B], ints[B:2 * B], ints[2 * B:3 * B],
+                       ints[5 * B:5 * B + B * D].view(B, D), ints[5 * B + B * D:].view(B, D),
+                       ints[3 * B:4 * B], ints[4 * B:5 * B])
+    res.ints = ints
+    if want_row:
+        res.sample_p = torch.empty(B, V, dtype=torch.float32, device=dev)
+    aout = _abi.AcceptOut()
+    aout.accept_length, aout.best_candidate, aout.token = _ptr(res.accept_length), _ptr(res.best_candidate), _ptr(res.token)
+    aout.path_tokens, aout.select_indices = _ptr(res.path_tokens), _ptr(res.select_indices)
+    aout.n_draws, aout.flags, aout.sample_p = _ptr(res.n_draws), _ptr(res.flags), _ptr(res.sample_p)
+    work = torch.empty(max(int(self.lib.lantern_accept_greedy_workspace_bytes(C.byref(cfg))), 4), dtype=torch.uint8,
+                       device=dev)
+    _abi.check(self.lib.lantern_accept_greedy(C.byref(cfg), C.byref(ain), C.byref(aout), work.data_ptr(), work.numel(),
+                                              torch.cuda.current_stream(dev).cuda_stream))
+    res._keepalive = (logits_cond, logits_uncond, tree_tokens, retrieve, work)
+    return res
+
+
+Verifier.greedy = _greedy
+
+
 def sample_tokens(probs: torch.Tensor, uniforms: torch.Tensor) -> torch.Tensor:
     """Inverse-CDF draw per row of ``probs`` [n, V] fp32 (the build's ``torch.multinomial(p, 1)``)."""
     lib = _abi.load()

@@ -127,6 +127,23 @@ def oracle_step(b: Built, keep_trace: bool = False) -> O.StepResult:
                          static=b.static, row_kinds=b.row_kinds, keep_trace=keep_trace)
 
 
+def oracle_greedy(b: Built):
+    """Greedy branches (``logits_processor is None``): tree_decoding post-processing + the [L, D, V] gather, then
+    ``evaluate_posterior_greedy`` / ``evaluate_posterior_greedy_lantern``.  Returns (best, accept_length, row, margin)."""
+    p = b.params
+    T = b.cond.shape[0]
+    rows = np.stack([O.cfg_mix(b.cond[n], b.uncond[n], p["cfg_scale"]) if b.uncond is not None
+                     else b.cond[n].astype(np.float32) for n in range(T)])
+    if b.fam.mask_non_image:
+        rows = np.stack([O.anole_mask_row(r, b.fam) for r in rows])
+    gathered = rows[np.asarray(b.tree.retrieve_indices, dtype=np.int64)]
+    if p["lantern"]:
+        k = min(int(p["lantern_k"]), b.fam.ncols - 1)
+        return O.evaluate_posterior_greedy_lantern(gathered, b.candidates, b.fam, b.table, k, p["lantern_delta"])
+    best, a, row = O.evaluate_posterior_greedy(gathered, b.candidates)
+    return best, a, row, 1.0
+
+
 def sample_p_probe(sample_p: np.ndarray, n: int = 48):
     """Compact fingerprint of a probability vector: its n largest entries + n hashed probes."""
     V = sample_p.shape[0]

@@ -270,9 +270,53 @@ def dynamic_tree_fixtures():
     return out
 
 
+GREEDY_CASES = [dict(family="anole", ncols=nc, top_k=0, temperature=0.0, lantern=lan, lantern_k=k, lantern_delta=d,
+                     seed=7000 + 13 * i + j, boost=bst, tree=tree, total_tokens=tt)
+                for i, (nc, k, d, bst, tree, tt) in enumerate([
+                    (1024, 100, 0.1, 9.0, "eagle2", 59), (1024, 100, 0.3, 9.0, "eagle2", 59),
+                    (2048, 1000, 0.1, 9.5, "eagle2", 59), (2048, 10, 5.0, 9.5, "eagle2", 59),
+                    (1024, 64, 2.0, 9.0, "random", 24), (4096, 300, 0.2, 10.0, "eagle2", 40)])
+                for j in range(4) for lan in (True, False)] + [
+    dict(family="anole", top_k=0, temperature=0.0, lantern=True, lantern_k=1000, lantern_delta=0.1, seed=7900, boost=11.0)]
+
+
+def greedy_fixtures(R):
+    """Greedy branches (logits_processor is None) of the live reference: ea_model_anole.py:789-902 with and without
+    the LANTERN relaxation, on Anole-shaped inputs (int64 table, offset 4, finfo.min mask)."""
+    kept, dropped = [], 0
+    for p in GREEDY_CASES:
+        b = C.build(C.default_params(**p))
+        logits = reference_tree_logits(R, b)
+        cand = torch.from_numpy(b.candidates)
+        k = min(int(p["lantern_k"]), b.fam.ncols - 1)
+        tbl = b.table.astype(np.int64) if b.table is not None else None
+        me = NS(nearest_latents=tbl, image_token_offset=b.fam.offset)
+        best, alen, row = R.anole.EaModel.evaluate_posterior(me, logits.clone(), cand, None, lantern=p["lantern"],
+                                                             lantern_k=k, lantern_delta=p["lantern_delta"])
+        if p["lantern"]:
+            ob, oa, orow, margin = O.evaluate_posterior_greedy_lantern(logits.numpy(), b.candidates, b.fam, b.table, k,
+                                                                       p["lantern_delta"])
+        else:
+            ob, oa, orow = O.evaluate_posterior_greedy(logits.numpy(), b.candidates)
+            margin = 1.0
+        if margin < MARGIN:
+            dropped += 1
+            continue
+        assert (int(best), int(alen)) == (ob, oa) and np.array_equal(row.numpy(), orow), ("ORACLE MISMATCH", p)
+        kept.append({"params": C.default_params(**p), "best_candidate": int(best), "accept_length": int(alen),
+                     "token": int(row.argmax()), "row_sum": float(row.double().clamp(min=-1e30).sum()),
+                     "input_checksum": float(b.cond.astype(np.float64).sum())})
+    return {"meta": {"generator": "tests/golden/gen_golden.py greedy_fixtures", "dropped_fragile": dropped,
+                     "n_cases": len(kept)}, "cases": kept}
+
+
 def main():
     torch.set_num_threads(max(1, os.cpu_count() or 1))
     R = import_reference()
+    with open(os.path.join(HERE, "greedy_cases.json"), "w") as f:
+        json.dump(greedy_fixtures(R), f)
+    if "--greedy-only" in sys.argv:
+        return
     with open(os.path.join(HERE, "dynamic_trees.json"), "w") as f:
         json.dump(dynamic_tree_fixtures(), f)
     kept, dropped, mismatched, worst_sp = [], 0, 0, 0.0

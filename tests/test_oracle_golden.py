@@ -17,6 +17,10 @@ with open(os.path.join(HERE, "golden", "tree_buffers.json")) as f:
     TREES = json.load(f)
 
 
+with open(os.path.join(HERE, "golden", "greedy_cases.json")) as f:
+    GREEDY = json.load(f)
+
+
 def _id(c):
     p = c["params"]
     return f"{p['family']}-{p['static_tree'] or p['tree']}-s{p['seed']}"
@@ -44,6 +48,17 @@ def test_oracle_matches_reference(case):
     assert np.all(got[~nz] == 0)
     assert np.max(np.abs(got[nz] - val[nz]) / val[nz]) <= 1e-5     # north_star: 1e-5 relative in fp32
     assert abs(float(r.sample_p.astype(np.float64).sum()) - case["sp_sum"]) <= 1e-5
+
+
+@pytest.mark.parametrize("case", GREEDY["cases"], ids=lambda c: f"greedy-{'lantern' if c['params']['lantern'] else 'plain'}-s{c['params']['seed']}")
+def test_oracle_greedy_matches_reference(case):
+    """Greedy branches of the live reference (ea_model_anole.py:789-902), with and without the relaxation."""
+    b = C.build(case["params"])
+    assert float(b.cond.astype(np.float64).sum()) == case["input_checksum"], "synthetic inputs drifted"
+    best, a, row, _ = C.oracle_greedy(b)
+    assert (best, a) == (case["best_candidate"], case["accept_length"])
+    assert int(row.argmax()) == case["token"]
+    assert float(np.maximum(row.astype(np.float64), -1e30).sum()) == pytest.approx(case["row_sum"], rel=1e-12)
 
 
 @pytest.mark.parametrize("name", CH.NAMES)

@@ -512,8 +512,10 @@ class VerifyMixin:
     def evaluate_posterior_v1(self, logits, candidates, logits_processor, cart_candidates_prob, op, p_indices,
                               tree_candidates, b_indices, lantern=False, lantern_k=1000, lantern_delta=0.1):
         """ea_model_llamagen.py:463-669 / ea_model_anole.py:464-669 (static tree, LANTERN++)."""
-        if logits_processor is None:
-            raise NotImplementedError("greedy static-tree decoding is not on the BASELINE path")
+        if logits_processor is None:     # same greedy code as the dynamic method (ea_model_anole.py:478-595)
+            return _verify_greedy(self._family(logits.shape[-1]), logits, candidates, lantern=lantern,
+                                  lantern_k=lantern_k, lantern_delta=lantern_delta,
+                                  nearest_latents=getattr(self, "nearest_latents", None))
         t, p, k = _warp_knobs(logits_processor)
         fam = self._family(logits.shape[-1])
         fused = isinstance(logits, TreeLogits)

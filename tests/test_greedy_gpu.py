@@ -106,3 +106,28 @@ def test_greedy_dropin_methods():
             masked[:, 4:4 + 1024] = mixed[:, 4:4 + 1024]
             gb2, ga2, grow2 = m.evaluate_posterior(masked[ri], cand, None, lantern=True, lantern_k=100, lantern_delta=0.2)
             assert (int(gb2), int(ga2)) == (best, a)
+
+
+def test_greedy_static_tree_v1_method():
+    """evaluate_posterior_v1(logits_processor=None) runs the same greedy code on a static tree (ea_model_anole.py:478-595)."""
+    class M(PO.VerifyMixin):
+        lantern_family = "anole"
+        lantern_image_tokens = 1024
+    dev = torch.device("cuda")
+    seed = 85000
+    while True:
+        b = C.build(dict(family="anole", ncols=1024, top_k=0, temperature=0.0, lantern=True, lantern_k=50,
+                         lantern_delta=0.3, boost=8.0, static_tree="mc_sim_7b_63", seed=seed))
+        seed += 1
+        best, a, row, margin = C.oracle_greedy(b)
+        if margin >= 1e-5 and a >= 1:
+            break
+    m = M()
+    m.nearest_latents = b.table.astype(np.int64)
+    m.image_token_offset = 4
+    tl = torch.from_numpy(np.stack([b.cond, b.uncond])).to(dev)
+    ri = torch.from_numpy(np.asarray(b.tree.retrieve_indices)).to(dev)
+    handle = PO.TreeLogits(tl[:1], tl[1:2], float(b.params["cfg_scale"]), ri)
+    gb, ga, grow = m.evaluate_posterior_v1(handle, torch.from_numpy(b.candidates).to(dev), None, None, None, None, None,
+                                           None, lantern=True, lantern_k=50, lantern_delta=0.3)
+    assert (int(gb), int(ga)) == (best, a) and np.array_equal(grow.cpu().numpy(), row)

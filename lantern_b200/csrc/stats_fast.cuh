@@ -36,6 +36,7 @@ __global__ void __launch_bounds__(NT, (NT <= 512 ? 2 : 1)) row_stats_fast_kernel
   constexpr int NE = NQ * 4, NW = NT / 32, EB = Elem<DT>::kBytes;
   __shared__ FastSmem<NW> fs;
   __shared__ SelectSmem sm;   // slow path only
+  __shared__ float slow_scr[33];
   extern __shared__ __align__(128) unsigned char dyn_smem[];
   const lantern_accept_cfg& cfg = P.cfg;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -98,7 +99,7 @@ __global__ void __launch_bounds__(NT, (NT <= 512 ? 2 : 1)) row_stats_fast_kernel
     mbar_wait(&fs.mbar, parity);
     parity ^= 1;
     float s[NE];
-    float fsum = 0.f, fsq = 0.f, fmn = INFINITY, fmx = -INFINITY;
+    float fsum = 0.f, fsq = 0.f, fmx = -INFINITY;   // the minimum is only needed by the rare slow path: computed there
 #pragma unroll
     for (int q = 0; q < NQ; ++q) {
       const int e0 = (q * NT + tid) * 4;
@@ -111,15 +112,13 @@ __global__ void __launch_bounds__(NT, (NT <= 512 ? 2 : 1)) row_stats_fast_kernel
         s[q * 4 + j] = v;
         fsum += v;
         fsq = fmaf(v, v, fsq);
-        fmn = fminf(fmn, v);
         fmx = fmaxf(fmx, v);
       }
     }
     fsum = warp_reduce(fsum, OpSum());
     fsq = warp_reduce(fsq, OpSum());
-    fmn = -warp_reduce(-fmn, OpMaxF());
     fmx = warp_reduce(fmx, OpMaxF());
-    if (lane == 0) fs.st_part[warp] = make_float4(fsum, fsq, fmn, fmx);
+    if (lane == 0) fs.st_part[warp] = make_float4(fsum, fsq, 0.f, fmx);
     if (tid < 64) fs.hist[tid] = 0u;
     if (tid == 0) fs.list_n = 0;
     __syncthreads();   // B1: statistics partials visible; every thread has consumed the staged row
@@ -130,11 +129,11 @@ __global__ void __launch_bounds__(NT, (NT <= 512 ? 2 : 1)) row_stats_fast_kernel
       if (tid == 0) P.stats[row] = st;
       continue;
     }
-    fsum = 0.f; fsq = 0.f; fmn = INFINITY; fmx = -INFINITY;
+    fsum = 0.f; fsq = 0.f; fmx = -INFINITY;
 #pragma unroll
     for (int w = 0; w < NW; ++w) {
       const float4 pw = fs.st_part[w];
-      fsum += pw.x; fsq += pw.y; fmn = fminf(fmn, pw.z); fmx = fmaxf(fmx, pw.w);
+      fsum += pw.x; fsq += pw.y; fmx = fmaxf(fmx, pw.w);
     }
     const float m = fmx;
 
@@ -142,9 +141,10 @@ __global__ void __launch_bounds__(NT, (NT <= 512 ? 2 : 1)) row_stats_fast_kernel
     float thr = -INFINITY;
     if (P.do_topk) {
       bool found = false;
-      const bool finite = isfinite(fmn) && isfinite(fmx) && isfinite(fsq);
-      if (finite && fmn == fmx) { thr = fmx; found = true; }
-      if (!found && finite) {
+      // a -inf / +inf / NaN element makes the sum of squares non-finite, a constant row has an empty bracket
+      // (sd == 0): both are left to the slow path below
+      const bool finite = isfinite(fmx) && isfinite(fsq);
+      if (finite) {
         const float inv_n = 1.0f / (float)cfg.ncols;
         const float mean = fsum * inv_n;
         const float sd = sqrtf(fmaxf(fsq * inv_n - mean * mean, 0.f));
@@ -239,9 +239,11 @@ __global__ void __launch_bounds__(NT, (NT <= 512 ? 2 : 1)) row_stats_fast_kernel
       if (!found) {   // tiers 2 and 3 (rare): work on a copy so that s[] stays in registers
         __syncthreads();
         float tmp[NE];
+        float fmn = INFINITY;
 #pragma unroll
-        for (int e = 0; e < NE; ++e) tmp[e] = s[e];
-        thr = select_slow<NE>(tmp, cfg.top_k, fmn, fmx, sm);
+        for (int e = 0; e < NE; ++e) { tmp[e] = s[e]; fmn = fminf(fmn, s[e]); }
+        fmn = -block_reduce(-fmn, OpMaxF(), -INFINITY, slow_scr);
+        thr = (fmn == fmx) ? fmx : select_slow<NE>(tmp, cfg.top_k, fmn, fmx, sm);
         __syncthreads();
       }
       {   // remember where the quantile really was (in standard deviations) for the next row

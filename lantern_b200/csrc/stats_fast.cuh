@@ -140,7 +140,7 @@ __global__ void __launch_bounds__(NT, (NT <= 512 ? 2 : 1)) row_stats_fast_kernel
     // ---- exact top-k threshold ----
     float thr = -INFINITY;
     if (P.do_topk) {
-      bool found = false;
+      bool found = false, bracket_hit = false;
       // a -inf / +inf / NaN element makes the sum of squares non-finite, a constant row has an empty bracket
       // (sd == 0): both are left to the slow path below
       const bool finite = isfinite(fmx) && isfinite(fsq);
@@ -232,6 +232,7 @@ __global__ void __launch_bounds__(NT, (NT <= 512 ? 2 : 1)) row_stats_fast_kernel
               __syncthreads();   // B5
               thr = fs.kth;
               found = true;
+              bracket_hit = true;
             }
           }
         }
@@ -251,7 +252,12 @@ __global__ void __launch_bounds__(NT, (NT <= 512 ? 2 : 1)) row_stats_fast_kernel
         const float mean = fsum * inv_n;
         const float sd = sqrtf(fmaxf(fsq * inv_n - mean * mean, 0.f));
         const float z_obs = (thr - mean) / sd;
-        if (isfinite(z_obs)) { z_run = z_obs; win_run = P.win_sd; }
+        // bracket width: the width the sampling noise of the quantile calls for (P.win_sd) after a hit, doubled
+        // after every consecutive miss (rows whose shape the Gaussian prior describes badly)
+        if (isfinite(z_obs)) {
+          z_run = z_obs;
+          win_run = bracket_hit ? P.win_sd : fminf(P.win_sd_first, 2.0f * fmaxf(win_run, P.win_sd));
+        }
       }
     }
 

@@ -522,7 +522,15 @@ __global__ void __launch_bounds__(kWalkThreads) walk_kernel(const AcceptParams P
       }
       int idx = -1;
       const int* nb_row = nullptr;
-      if (cfg.lantern && relaxable) {
+      float qx = 1.0f;
+      if (cfg.static_tree) {
+        qx = P.in.node_q[(size_t)b * T + cnode];
+        if (qx <= 0.f) continue;   // the draw above is consumed first, like the reference (:636-638)
+      }
+      // The relaxation only ever adds mass (px += cs[idx] >= 0): a candidate that passes on its own probability is
+      // accepted whatever the neighbours hold, so their gather and scan are skipped for it.
+      const bool sure = r <= __fdiv_rn(px, qx);
+      if (cfg.lantern && relaxable && !sure) {
         nb_row = P.in.nbr_table + (size_t)(x - off) * cfg.table_cols;
         const float bound = cfg.lantern_delta > 1.0f ? __fmul_rn(cfg.lantern_delta_m1, px) : cfg.lantern_delta;
         double carry = 0.0;
@@ -552,11 +560,6 @@ __global__ void __launch_bounds__(kWalkThreads) walk_kernel(const AcceptParams P
           idx = n_ok - 1;
           px = __fadd_rn(px, S.fscr[35]);
         }
-      }
-      float qx = 1.0f;
-      if (cfg.static_tree) {
-        qx = P.in.node_q[(size_t)b * T + cnode];
-        if (qx <= 0.f) continue;
       }
       const float acp = __fdiv_rn(px, qx);
       if (r <= acp) {

@@ -530,9 +530,21 @@ __global__ void __launch_bounds__(kWalkThreads) walk_kernel(const AcceptParams P
       // The relaxation only ever adds mass (px += cs[idx] >= 0): a candidate that passes on its own probability is
       // accepted whatever the neighbours hold, so their gather and scan are skipped for it.
       const bool sure = r <= __fdiv_rn(px, qx);
-      if (cfg.lantern && relaxable && !sure) {
+      bool scan = cfg.lantern && relaxable && !sure;
+      float bound = 0.f;
+      if (scan) {
         nb_row = P.in.nbr_table + (size_t)(x - off) * cfg.table_cols;
-        const float bound = cfg.lantern_delta > 1.0f ? __fmul_rn(cfg.lantern_delta_m1, px) : cfg.lantern_delta;
+        bound = cfg.lantern_delta > 1.0f ? __fmul_rn(cfg.lantern_delta_m1, px) : cfg.lantern_delta;
+        // The added mass never exceeds the bound (cs[idx] <= bound, rounding is monotone), so a draw above
+        // (px + bound) / qx is a rejection whatever the neighbours hold.  The residual update then only needs to know
+        // whether any neighbour was aggregated (idx != -1), i.e. whether the first prefix sum is within the bound.
+        if (r > __fdiv_rn(__fadd_rn(px, bound), qx)) {
+          scan = false;
+          const float cs0 = (float)((double)prob_of(__ldg(nb_row) + off) * (double)scale);
+          idx = (kk > 0 && cs0 <= bound) ? 0 : -1;
+        }
+      }
+      if (scan) {
         double carry = 0.0;
         int n_ok = 0;
         for (int base_t = 0; base_t < kk; base_t += NT) {

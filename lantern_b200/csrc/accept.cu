@@ -190,7 +190,7 @@ struct WalkSmem {
   float* csv;        // [kWalkThreads] per-thread cumulative sums of the current neighbour chunk
   float* uni;        // [T + 1] this item's uniforms (supplied or Philox)
   int* sib;          // [kMaxSib] tokens of the rejected node's earlier siblings
-  int* pid;          // [D+1][L] prefix class of every row per level: smallest row with the same token prefix
+  int* pid;          // [L] rows still matching the accepted prefix
   double* dscr;      // [34]
   float* fscr;       // [34]
   int* iscr;         // [40]
@@ -370,7 +370,7 @@ __global__ void __launch_bounds__(kWalkThreads) walk_kernel(const AcceptParams P
   S.sib = reinterpret_cast<int*>(smem_raw + o);             o += kMaxSib * 4;
   S.fscr = reinterpret_cast<float*>(smem_raw + o);          o += 36 * 4;
   S.iscr = reinterpret_cast<int*>(smem_raw + o);            o += 40 * 4;
-  S.pid = reinterpret_cast<int*>(smem_raw + o);                 o += (size_t)(((D + 1) * L + 3) & ~3) * 4;
+  S.pid = reinterpret_cast<int*>(smem_raw + o);                 o += (size_t)((L + 3) & ~3) * 4;
   float* lazy_park = reinterpret_cast<float*>(smem_raw + o);   // [LNE][kWalkThreads] (lazy mode only)
   __shared__ SelectSmem lazy_sm;
   __shared__ float lazy_part[32];
@@ -392,31 +392,14 @@ __global__ void __launch_bounds__(kWalkThreads) walk_kernel(const AcceptParams P
     const int n = S.ri[j * D + i];
     return n >= 0 ? S.tok[n] : -1;
   };
-  // Prefix classes (once per item): pid[i][j] = smallest row j' whose tokens cand[j', 0:i] equal cand[j, 0:i].
-  // The reference's `is_eq` at level i (ea_model_llamagen.py:721) is "pid[i][j] == pid[i][best]"; a row is the first
-  // to offer its token at level i (the `candidates_set` dedup) iff pid[i+1][j] == j.
-  for (int j = tid; j < L; j += NT) S.pid[j] = 0;
-  __syncthreads();
+  // Rows still matching the accepted prefix (the reference's `is_eq`, ea_model_llamagen.py:721): every row that starts
+  // with row 0's root token; an acceptance at level i keeps the rows whose token at level i is the accepted one.
+  int* member = S.pid;   // [L]
   {
-    const int lane = tid & 31, warp = tid >> 5, nwarp = NT >> 5;
-    for (int i = 0; i < D; ++i) {   // one warp per row: the lanes scan the earlier rows with a ballot
-      const int* cur = S.pid + (size_t)i * L;
-      int* nxt = S.pid + (size_t)(i + 1) * L;
-      for (int j = warp; j < L; j += nwarp) {
-        const int cj = cur[j], xj = cand(j, i);
-        int rep = j;
-        for (int jb = cj; jb < j; jb += 32) {
-          const int jj = jb + lane;
-          const bool hit = jj < j && cur[jj] == cj && cand(jj, i) == xj;
-          const unsigned m = __ballot_sync(0xffffffffu, hit);
-          if (m) { rep = jb + __ffs(m) - 1; break; }
-        }
-        if (lane == 0) nxt[j] = rep;
-      }
-      __syncthreads();
-    }
+    const int root_tok = cand(0, 0);
+    for (int j = tid; j < L; j += NT) member[j] = cand(j, 0) == root_tok ? 1 : 0;
   }
-  int cls_cur = S.pid[(size_t)1 * L + 0];   // rows whose root token equals row 0's
+  __syncthreads();
 
   // ---- distribution state: window S.p + one explicit out-of-window token + uniform remainder ----
   // The residual is stored unnormalised: probability = stored value * scale.  A rejection then only zeroes
@@ -476,28 +459,33 @@ __global__ void __launch_bounds__(kWalkThreads) walk_kernel(const AcceptParams P
     // Warp 0 lists the distinct children of the current node in row order (the reference's `candidates_set`
     // dedup, ea_model_llamagen.py:728-739) and finds fi, the first row still matching the accepted prefix.
     if (tid < 32) {
-      int n = 0;
-      const int* cls_l = S.pid + (size_t)lvl * L;
-      const int* cls_n = S.pid + (size_t)(lvl + 1) * L;
+      int n = 0, first_member = -1;
       for (int jb = 0; jb < L; jb += 32) {
         const int j = jb + tid;
+        const bool mem = j < L && member[j] != 0;
+        const unsigned mm = __ballot_sync(0xffffffffu, mem);
+        if (first_member < 0 && mm) first_member = jb + __ffs(mm) - 1;
         int x = -1, cn = -1;
-        if (j < L && cls_l[j] == cls_cur && cls_n[j] == j) {
+        if (mem) {
           cn = S.ri[j * D + lvl];
           x = cn >= 0 ? S.tok[cn] : -1;
         }
-        const bool first = x != -1;
+        // first occurrence of the token: lowest lane of its match group in this chunk, and not listed by an earlier chunk
+        const unsigned peers = __match_any_sync(0xffffffffu, x != -1 ? x : -2 - tid);
+        bool first = x != -1 && tid == __ffs(peers) - 1;
+        for (int q = 0; q < n; ++q) first = first && (S.tried[q] != x);
         const unsigned mf = __ballot_sync(0xffffffffu, first);
         if (first) {
           const int pos = n + __popc(mf & ((1u << tid) - 1u));
           S.tried[pos] = x; S.kid_j[pos] = j; S.kid_node[pos] = cn;
         }
         n += __popc(mf);
+        __syncwarp();
       }
-      if (tid == 0) S.iscr[38] = n;
+      if (tid == 0) { S.iscr[38] = n; S.iscr[35] = first_member < 0 ? 0 : first_member; }
     }
     __syncthreads();
-    const int n_kids = S.iscr[38], fi = cls_cur;   // the class representative is its first row
+    const int n_kids = S.iscr[38], fi = S.iscr[35];   // fi: first row still matching the accepted prefix
     if (cfg.lantern && tid < n_kids) {   // pull the children's neighbour-table rows towards L2 behind the row load
       const int xk = S.tried[tid] - off;
       if (xk >= 0 && xk < ncols) {
@@ -575,10 +563,11 @@ __global__ void __launch_bounds__(kWalkThreads) walk_kernel(const AcceptParams P
       }
       const float acp = __fdiv_rn(px, qx);
       if (r <= acp) {
-        cls_cur = j;   // == pid[lvl + 1][j]: rows that continue with token x
         ++accept_length;
         best = j;
         accepted = true;
+        for (int jj = tid; jj < L; jj += NT)     // rows that continue with token x
+          if (member[jj] && cand(jj, lvl) != x) member[jj] = 0;
         __syncthreads();
         break;
       }
@@ -764,7 +753,7 @@ static size_t walk_smem_bytes(const lantern_accept_cfg& c, int lazy_ne) {
   o += (size_t)kWalkThreads * 4;
   o += (size_t)((c.n_rows + 4) & ~3) * 4;
   o += kMaxSib * 4 + 36 * 4 + 40 * 4;
-  o += (size_t)((((c.depth + 1) * c.n_paths) + 3) & ~3) * 4 + 16;
+  o += (size_t)((c.n_paths + 3) & ~3) * 4 + 16;
   return o;
 }
 

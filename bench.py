@@ -430,7 +430,7 @@ def run_b200(args):
             "verify_steps_per_s": world * B * args.steps / (ms_all * 1e-3),
             "accept_step_gbs": step_bytes / (ms_all / args.steps * 1e-3) / 1e9,
             "clocks": clocks.summary(),
-            "gpu_launches": (1 if default_phases == 6 or (default_phases == 8 and B * T >= 2048 and fam.ncols in (4096, 8192, 16384, 32768)) else 2) * args.steps,
+            "gpu_launches": (1 if default_phases == 6 or (default_phases == 8 and B * T >= 2048 and fam.ncols in (2048, 4096, 8192, 16384)) else 2) * args.steps,
             "roofline": {"bound": "hbm", "kernel": "row_stats_fast_kernel", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst; kernel timed alone)" if peaks else "fallback 6650 GB/s",

@@ -29,6 +29,7 @@
 namespace lantern {
 
 constexpr int kWalkThreads = 1024;
+constexpr int kLazyThreads = 512;   // lazy schedule: fewer, fatter threads (16 row values each at 8192 columns) and cheaper barriers
 constexpr int kMaxSib = 64;
 
 
@@ -267,7 +268,7 @@ __device__ __forceinline__ RowStats raw_row_stats(const AcceptParams& P, int b, 
 template <int DT, int NE>
 __device__ __forceinline__ void lazy_probs(const AcceptParams& P, int b, int node, bool raw, float* p, float* park,
                                            SelectSmem& sm, float* part_scr, float& z_run, float& win_run) {
-  constexpr int NT = kWalkThreads, NW = NT / 32, NQ = NE / 4;
+  constexpr int NT = kLazyThreads, NW = NT / 32, NQ = NE / 4;
   const lantern_accept_cfg& cfg = P.cfg;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int64_t base = (int64_t)b * cfg.item_stride + (int64_t)node * cfg.row_stride + cfg.col0;
@@ -346,7 +347,7 @@ __device__ __forceinline__ void lazy_probs(const AcceptParams& P, int b, int nod
 }
 
 template <int DT, bool VEC, int LNE>
-__global__ void __launch_bounds__(kWalkThreads) walk_kernel(const AcceptParams P) {
+__global__ void __launch_bounds__(LNE > 0 ? kLazyThreads : kWalkThreads) walk_kernel(const AcceptParams P) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const lantern_accept_cfg& cfg = P.cfg;
   const int b = blockIdx.x, tid = threadIdx.x, NT = blockDim.x;
@@ -371,7 +372,7 @@ __global__ void __launch_bounds__(kWalkThreads) walk_kernel(const AcceptParams P
   S.fscr = reinterpret_cast<float*>(smem_raw + o);          o += 36 * 4;
   S.iscr = reinterpret_cast<int*>(smem_raw + o);            o += 40 * 4;
   S.pid = reinterpret_cast<int*>(smem_raw + o);                 o += (size_t)((L + 3) & ~3) * 4;
-  float* lazy_park = reinterpret_cast<float*>(smem_raw + o);   // [LNE][kWalkThreads] (lazy mode only)
+  float* lazy_park = reinterpret_cast<float*>(smem_raw + o);   // [LNE][kLazyThreads] (lazy mode only)
   __shared__ SelectSmem lazy_sm;
   __shared__ float lazy_part[32];
   float z_run = P.z_guess, win_run = P.win_sd_first;
@@ -743,7 +744,7 @@ __global__ void __launch_bounds__(kWalkThreads) walk_kernel(const AcceptParams P
 // Host side
 // ----------------------------------------------------------------------------------------------
 static size_t walk_smem_bytes(const lantern_accept_cfg& c, int lazy_ne) {
-  size_t o = (size_t)lazy_ne * kWalkThreads * 4;
+  size_t o = (size_t)lazy_ne * kLazyThreads * 4;
   o += (size_t)((c.ncols + 3) & ~3) * 4;
   o += (size_t)((((c.ncols + 31) >> 5) + 3) & ~3) * 4;
   o += 34 * 8;
@@ -764,8 +765,8 @@ static int launch_all(const AcceptParams& P, cudaStream_t stream, int phases) {
   if (phases & 8) {
     // automatic policy (measured, profiles/sweep_r1.md): streaming every tree row pays off while the step is
     // latency-bound; from ~2K rows on, computing the statistics of the visited rows inside the walk is faster
-    const int ne = c.ncols / kWalkThreads;
-    const bool lazy_ok = VEC && !P.do_topp && c.ncols % (4 * kWalkThreads) == 0 && (ne == 4 || ne == 8 || ne == 16 || ne == 32);
+    const int ne = c.ncols / kLazyThreads;
+    const bool lazy_ok = VEC && !P.do_topp && c.ncols % (4 * kLazyThreads) == 0 && (ne == 4 || ne == 8 || ne == 16 || ne == 32);
     phases = (lazy_ok && rows >= 2048) ? 6 : 3;
   }
   const int nquads = (c.ncols + 3) / 4;
@@ -859,12 +860,12 @@ static int launch_all(const AcceptParams& P, cudaStream_t stream, int phases) {
   if (!(phases & 2)) return LANTERN_OK;
   // lazy mode (phases bit 2): the walk computes the statistics of the rows it visits itself
   int lazy_ne = 0;
-  if ((phases & 4) && VEC && !P.do_topp && c.ncols % (4 * kWalkThreads) == 0) {
-    const int ne = c.ncols / kWalkThreads;
+  if ((phases & 4) && VEC && !P.do_topp && c.ncols % (4 * kLazyThreads) == 0) {
+    const int ne = c.ncols / kLazyThreads;
     if (ne == 4 || ne == 8 || ne == 16 || ne == 32) lazy_ne = ne;
   }
   if ((phases & 4) && !lazy_ne) {
-    set_error("lazy statistics need a vector-aligned window of 4096/8192/16384/32768 columns and no top-p");
+    set_error("lazy statistics need a vector-aligned window of 2048/4096/8192/16384 columns and no top-p");
     return LANTERN_E_UNSUPPORTED;
   }
   const size_t smem = walk_smem_bytes(c, lazy_ne);
@@ -877,7 +878,7 @@ static int launch_all(const AcceptParams& P, cudaStream_t stream, int phases) {
     auto kern = walk_kernel<DT, V, NE>;                                                             \
     if (smem > 48 * 1024)                                                                           \
       LANTERN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    kern<<<c.n_items, kWalkThreads, smem, stream>>>(P);                                             \
+    kern<<<c.n_items, (NE) > 0 ? kLazyThreads : kWalkThreads, smem, stream>>>(P);                   \
   } while (0)
   switch (lazy_ne) {
     case 0: LAUNCH_WALK(VEC, 0); break;

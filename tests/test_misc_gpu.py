@@ -94,7 +94,7 @@ def test_host_buffer_session_matches_oracle(family, kw, pinned):
             orcs.append(o)
     out, path, sel, sp = _session_step(built, want_sample_p=True, pinned=pinned)
     # page-locked logits with a lazy-eligible window are read in place (zero-copy); everything else is staged
-    lazy_ok = built[0].fam.ncols in (4096, 8192, 16384, 32768)
+    lazy_ok = built[0].fam.ncols in (2048, 4096, 8192, 16384)
     assert out["route"] == (1 if pinned and lazy_ok else 0)
     for i, o in enumerate(orcs):
         a = int(out["accept_length"][i])

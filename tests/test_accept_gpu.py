@@ -8,6 +8,8 @@ import torch
 
 import casegen as C
 import cuda_runner as R
+from lantern_b200 import verify
+from oracle import lantern_oracle as O
 
 pytestmark = pytest.mark.gpu
 
@@ -271,3 +273,46 @@ def test_lumina_bf16_window_misaligned_for_16_bytes(dtype):
     res = R.run_cases(built, dtype=dtype)
     for i, o in enumerate(orcs):
         R.compare(res, i, o)
+
+
+@pytest.mark.parametrize("dist", ["gauss", "student_t2", "bimodal", "lognormal", "quantised", "mixed_rows"])
+@pytest.mark.parametrize("ncols,top_k", [(8192, 2000), (16384, 2000), (4096, 50)])
+def test_row_statistics_exact_on_non_gaussian_rows(dist, ncols, top_k):
+    """The tracked-quantile bracket is a speed heuristic; the threshold must stay the exact k-th largest (ties kept)
+    and the softmax statistics right for any row shape.  Reads the RowStats workspace of a phases=1 launch."""
+    rng = np.random.default_rng(hash((dist, ncols)) % 2**32)
+    B, T = 5, 33
+    shape = (B, T, ncols)
+    if dist == "gauss":
+        x = rng.standard_normal(shape) * 2.5
+    elif dist == "student_t2":
+        x = rng.standard_t(2, shape)
+    elif dist == "bimodal":
+        x = np.where(rng.random(shape) < 0.3, rng.standard_normal(shape) + 6, rng.standard_normal(shape) * 0.3 - 4)
+    elif dist == "lognormal":
+        x = rng.lognormal(0.0, 1.5, shape)
+    elif dist == "quantised":
+        x = np.round(rng.standard_normal(shape) * 3) / 2.0                  # ~30 distinct values: massive ties
+    else:                                                                    # the shape changes from row to row
+        x = rng.standard_normal(shape) * rng.uniform(0.1, 8.0, (B, T, 1)) + rng.uniform(-20, 20, (B, T, 1))
+        x[:, ::5] = rng.standard_t(1.5, (B, len(range(0, T, 5)), ncols))
+    cond = x.astype(np.float32)
+    uncond = (x + rng.standard_normal(shape) * 0.7).astype(np.float32)
+    fam = verify.LLAMAGEN.resized(ncols)
+    v = verify.Verifier(fam, temperature=1.0, top_k=top_k, cfg_scale=3.0, lantern=False, device=torch.device("cuda"))
+    tokens = torch.zeros(B, T, dtype=torch.int32, device="cuda")
+    retrieve = torch.zeros(B, 1, 1, dtype=torch.int32, device="cuda")
+    v.step(torch.from_numpy(cond).cuda(), torch.from_numpy(uncond).cuda(), tokens, retrieve,
+           uniforms=torch.rand(B, 2, device="cuda"), phases=1)
+    torch.cuda.synchronize()
+    stats = v._work[:B * T * 32].view(torch.float32).view(B * T, 8).cpu().numpy()
+    s = O.cfg_mix(cond.reshape(-1, ncols), uncond.reshape(-1, ncols), 3.0)
+    kth = np.partition(s, ncols - top_k, axis=1)[:, ncols - top_k]
+    assert np.array_equal(stats[:, 0], kth), f"{int((stats[:, 0] != kth).sum())} thresholds differ"
+    assert np.array_equal(stats[:, 1], s.max(axis=1))
+    kept = s >= kth[:, None]
+    want = (np.exp((s - s.max(axis=1, keepdims=True)).astype(np.float64)) * kept).sum(axis=1)
+    # the stored sum carries the rounding of max*log2(e) as a common factor (it cancels in every probability, which is
+    # formed with the same constant): allow 2^-24 * |max| * log2(e) on top of the 2e-6 of the exp itself
+    tol = 2e-6 + 1.0e-7 * 1.45 * np.abs(s.max(axis=1))
+    assert np.all(np.abs(stats[:, 2] - want) / want < tol)

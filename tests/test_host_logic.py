@@ -85,3 +85,13 @@ def test_lumina_row_kinds():
     got = PO.lumina_row_kinds(pos, 7).numpy()
     want = O.lumina_row_kinds(pos.numpy(), 7)
     assert np.array_equal(got, want) and (got == 1).sum() >= 47 and (got == 2).sum() == 1
+
+
+def test_every_exported_entry_is_documented():
+    """INTEGRATION.md names every LANTERN_API symbol of the header (the table a reference maintainer binds against)."""
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    header = open(os.path.join(root, "include", "lantern_b200.h")).read()
+    names = set(re.findall(r"LANTERN_API\s+[\w\s\*]+?\b(lantern_\w+)\s*\(", header))
+    doc = open(os.path.join(root, "INTEGRATION.md")).read()
+    assert names and not [n for n in names if n not in doc]

@@ -502,6 +502,20 @@ __global__ void __launch_bounds__(LNE > 0 ? kLazyThreads : kWalkThreads) walk_ke
     bool accepted = false;
     for (int c = 0; c < n_kids && !accepted; ++c) {
       const int j = S.kid_j[c], cnode = S.kid_node[c], x = S.tried[c];
+      // If this child is accepted its own logits row is the next one the walk needs: pull it towards L2 now, behind
+      // the neighbour gather and the scan (a wasted prefetch costs 64 KiB of otherwise idle HBM bandwidth).
+      if (P.prefetch_rows && tid == 0 && cnode >= 0 && lvl + 1 < D) {
+        constexpr size_t eb = Elem<DT>::kBytes;
+        const int64_t nbase = (int64_t)b * cfg.item_stride + (int64_t)cnode * cfg.row_stride + col0;
+        const uintptr_t a0 = (reinterpret_cast<uintptr_t>(P.in.logits_cond) + nbase * eb + 15) & ~uintptr_t(15);
+        const uintptr_t a1 = (reinterpret_cast<uintptr_t>(P.in.logits_cond) + (nbase + ncols) * eb) & ~uintptr_t(15);
+        if (a1 > a0) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a0), "r"((unsigned)(a1 - a0)));
+        if (P.mix.has_uncond) {
+          const uintptr_t b0 = (reinterpret_cast<uintptr_t>(P.in.logits_uncond) + nbase * eb + 15) & ~uintptr_t(15);
+          const uintptr_t b1 = (reinterpret_cast<uintptr_t>(P.in.logits_uncond) + (nbase + ncols) * eb) & ~uintptr_t(15);
+          if (b1 > b0) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(b0), "r"((unsigned)(b1 - b0)));
+        }
+      }
       const float r = uniform(draws++);
       float px = __fmul_rn(prob_of(x), scale);
       bool relaxable = true;
@@ -759,7 +773,9 @@ static size_t walk_smem_bytes(const lantern_accept_cfg& c, int lazy_ne) {
 }
 
 template <int DT, bool VEC>
-static int launch_all(const AcceptParams& P, cudaStream_t stream, int phases) {
+static int launch_all(const AcceptParams& P_in, cudaStream_t stream, int phases) {
+  AcceptParams P = P_in;
+  P.prefetch_rows = (phases & 16) ? 0 : 1;   // bit 4: logits live behind PCIe (in-place host rows): no speculative reads
   const lantern_accept_cfg& c = P.cfg;
   const long long rows = (long long)c.n_items * c.n_rows;
   if (phases & 8) {

@@ -239,7 +239,7 @@ extern "C" int lantern_session_step(lantern_session* s, const lantern_accept_cfg
     lantern_accept_in hi = di;
     hi.logits_cond = dev_cond;
     hi.logits_uncond = in->logits_uncond ? dev_uncond : nullptr;
-    rc = lantern_accept_phases(&hc, &hi, &dout, s->d_work, s->work_bytes, st, 6);
+    rc = lantern_accept_phases(&hc, &hi, &dout, s->d_work, s->work_bytes, st, 6 | 16);   // lazy, no speculative row reads
     if (rc == LANTERN_OK) s->last_in_place = 1;
     else if (rc == LANTERN_E_UNSUPPORTED) {   // not lazy-eligible: stage the window after all
       LANTERN_CUDA(copy_rows(s->d_cond, in->logits_cond));

@@ -69,14 +69,14 @@ def _seeded_uniforms(seed, T):
     return u, ub
 
 
-def _run_case(case, fused):
+def _run_case(case, fused, rng_seed=None):
     dev = torch.device("cuda")
     p = case["params"]
     b = C.build(p)
     fam = b.fam
     L, D = b.candidates.shape
     T_draw = b.tree.T if fused else L * D
-    u, ub = _seeded_uniforms(p["seed"], T_draw)
+    u, ub = _seeded_uniforms(p["seed"] if rng_seed is None else rng_seed, T_draw)
     static = b.static is not None
     cand = torch.from_numpy(b.candidates).to(dev)
     if fused:
@@ -132,9 +132,13 @@ SUPPORTED = lambda p: True
 def test_mixin_matches_reference_decisions(case, fused):
     """Golden outputs were produced by the live reference with uniforms[:n]; here the shim draws its own uniforms
     from python `random`, so the check is against the oracle on those uniforms."""
-    best, a, sample_p, orc, u, _ = _run_case(case, fused)
-    if orc.margin < 1e-5:
-        pytest.skip("fragile decision margin")
+    # a draw that lands within 1e-5 of a decision boundary depends on the last ulp of exp: re-seed the module RNG
+    for attempt in range(6):
+        best, a, sample_p, orc, u, _ = _run_case(case, fused, rng_seed=case["params"]["seed"] + 7919 * attempt)
+        if orc.margin >= 1e-5:
+            break
+    else:
+        pytest.skip("fragile decision margin for six different uniform streams")
     assert isinstance(best, torch.Tensor) and best.dim() == 0 and best.dtype == torch.int64 and best.device.type == "cpu"
     assert isinstance(a, int)
     assert int(best) == orc.best_candidate and a == orc.accept_length

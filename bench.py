@@ -222,7 +222,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 def workload_config(args, items):
@@ -454,7 +454,7 @@ def run_b200(args):
                                               f"oracle/lantern_oracle.py eager, one process per core ({wall:.1f}s wall)"}
         if not args.no_torch and world == 1:
             line["torch_gpu_baseline"] = torch_gpu_baseline(args, fam, batches[0], results and run(0), table_np, k, tpi)
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -549,7 +549,22 @@ def run_e2e(args, fam, ver, table_np, tree_pool, rank, dev, world):
             "l2_policy": "L2 flushed (256 MB memset) before every step, outside the timed region"}
 
 
+_JSON_OUT = None
+
+
+def emit(line):
+    """The one JSON line of the contract, written to the process's original stdout."""
+    out = _JSON_OUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 if __name__ == "__main__":
+    # Libraries chat on stdout (NCCL prints its version there at NCCL_DEBUG=VERSION/WARN): keep the original stdout
+    # for the JSON line only and send everything else to stderr.
+    sys.stdout.flush()
+    _JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     a = parse()
     if a.impl == "reference":
         run_reference(a)

@@ -310,9 +310,29 @@ def greedy_fixtures(R):
                      "n_cases": len(kept)}, "cases": kept}
 
 
+def signature_fixture(R):
+    """Parameter lists of the reference's call surface for tests/test_host_logic.py."""
+    import inspect
+
+    def sig(f):
+        return [[n, (None if p.default is inspect._empty else repr(p.default))]
+                for n, p in inspect.signature(f).parameters.items()]
+    out = {f"utils.{n}": sig(getattr(R.utils, n)) for n in
+           ("tree_decoding", "evaluate_posterior", "update_inference_inputs", "prepare_logits_processor",
+            "generate_tree_buffers")}
+    for fam, mod in (("llamagen", R.llamagen), ("anole", R.anole)):
+        for m in ("tree_decoding", "evaluate_posterior", "evaluate_posterior_v1", "update_inference_inputs"):
+            out[f"{fam}.EaModel.{m}"] = sig(getattr(mod.EaModel, m))
+    for m in ("tree_decoding", "evaluate_posterior", "update_inference_inputs"):
+        out[f"lumina.EaLumina_mGPT.{m}"] = sig(getattr(R.lumina.EaLumina_mGPT, m))
+    return out
+
+
 def main():
     torch.set_num_threads(max(1, os.cpu_count() or 1))
     R = import_reference()
+    with open(os.path.join(HERE, "signatures.json"), "w") as f:
+        json.dump(signature_fixture(R), f, indent=1)
     with open(os.path.join(HERE, "greedy_cases.json"), "w") as f:
         json.dump(greedy_fixtures(R), f)
     if "--greedy-only" in sys.argv:

@@ -95,3 +95,34 @@ def test_every_exported_entry_is_documented():
     names = set(re.findall(r"LANTERN_API\s+[\w\s\*]+?\b(lantern_\w+)\s*\(", header))
     doc = open(os.path.join(root, "INTEGRATION.md")).read()
     assert names and not [n for n in names if n not in doc]
+
+
+def test_dropin_signatures_match_reference():
+    """the shims keep the reference's call signatures.  tests/golden/signatures.json holds the parameter
+    lists of the live reference methods (written by inspect in the build container); every reference parameter must
+    exist here under the same name, in the same relative order, and the required positional prefix must be identical."""
+    import inspect
+    import json
+    from lantern_b200 import trees
+    here = os.path.dirname(os.path.abspath(__file__))
+    ref = json.load(open(os.path.join(here, "golden", "signatures.json")))
+    ours = {
+        "utils.tree_decoding": PO.tree_decoding, "utils.evaluate_posterior": PO.evaluate_posterior,
+        "utils.update_inference_inputs": PO.update_inference_inputs,
+        "utils.prepare_logits_processor": PO.prepare_logits_processor,
+        "utils.generate_tree_buffers": trees.generate_tree_buffers,
+        "lumina.EaLumina_mGPT.tree_decoding": PO.LuminaVerifyMixin.tree_decoding,
+        "lumina.EaLumina_mGPT.evaluate_posterior": PO.LuminaVerifyMixin.evaluate_posterior,
+        "lumina.EaLumina_mGPT.update_inference_inputs": PO.LuminaVerifyMixin.update_inference_inputs,
+    }
+    for fam in ("llamagen", "anole"):
+        for m in ("tree_decoding", "evaluate_posterior", "evaluate_posterior_v1", "update_inference_inputs"):
+            ours[f"{fam}.EaModel.{m}"] = getattr(PO.VerifyMixin, m)
+    assert set(ours) == set(ref)
+    for name, f in ours.items():
+        mine = list(inspect.signature(f).parameters)
+        theirs = [p for p, _ in ref[name]]
+        required = [p for p, d in ref[name] if d is None]
+        assert mine[:len(required)] == required, (name, mine, required)
+        pos = [mine.index(p) for p in theirs]                 # raises if a reference parameter is missing
+        assert pos == sorted(pos), (name, mine, theirs)

@@ -241,6 +241,32 @@ def workload_config(args, items):
 # ------------------------------------------------------------------------------------------------
 # B200 arm
 # ------------------------------------------------------------------------------------------------
+def bind_to_gpu_numa(local):
+    """Pin this rank's host threads (and therefore its first-touch pinned buffers) to the NUMA node of its GPU, so that
+    the in-place PCIe reads of the host-buffer route do not cross sockets when several ranks run on one box."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(local)).busId
+        bus = (bus.decode() if isinstance(bus, bytes) else bus).lower()
+        if len(bus.split(":")[0]) > 4:
+            bus = bus[-12:]                               # nvml pads the PCI domain to 8 hex digits
+        node = int(open(f"/sys/bus/pci/devices/{bus}/numa_node").read())
+        if node < 0:
+            return None
+        cpus = []
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.extend(range(int(a), int(b or a) + 1))
+        allowed = sorted(set(cpus) & set(os.sched_getaffinity(0)))
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+            return node
+    except Exception:
+        pass
+    return None
+
+
 def run_b200(args):
     import torch
     import torch.distributed as dist
@@ -254,6 +280,7 @@ def run_b200(args):
         raise SystemExit("bench.py: no CUDA device (the B200 arm has no CPU fallback)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa = bind_to_gpu_numa(local) if world > 1 else None
     if world > 1:
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=dev)
@@ -430,6 +457,7 @@ def run_b200(args):
             "verify_steps_per_s": world * B * args.steps / (ms_all * 1e-3),
             "accept_step_gbs": step_bytes / (ms_all / args.steps * 1e-3) / 1e9,
             "clocks": clocks.summary(),
+            "host_numa_node_rank0": numa,
             "gpu_launches": (1 if default_phases == 6 or (default_phases == 8 and B * T >= 2048 and fam.ncols in (2048, 4096, 8192, 16384)) else 2) * args.steps,
             "roofline": {"bound": "hbm", "kernel": "row_stats_fast_kernel", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,

@@ -548,21 +548,31 @@ __global__ void __launch_bounds__(LNE > 0 ? kLazyThreads : kWalkThreads) walk_ke
         }
       }
       if (scan) {
+        // Prefix sums of the neighbour masses in fp64 (rounded to fp32 per prefix, like the CPU cumsum), in chunks of
+        // EPT * NT neighbours: each thread owns EPT consecutive neighbours, so the usual k = 1000 is one block scan for
+        // both CTA sizes (1024 threads x 1, 512 threads x 2).
+        const int ept = kk > NT ? 2 : 1;
+        const int span = NT * ept;
         double carry = 0.0;
         int n_ok = 0;
-        for (int base_t = 0; base_t < kk; base_t += NT) {
-          const int tt = base_t + tid;
-          const int chunk = min(NT, kk - base_t);
+        for (int base_t = 0; base_t < kk; base_t += span) {
+          const int chunk = min(span, kk - base_t);
           if (tid == 0) S.iscr[39] = chunk;             // index (within the chunk) of the first sum above the bound
-          double v = 0.0;
-          if (tt < kk) v = (double)prob_of(__ldg(nb_row + tt) + off);
+          const int t0 = base_t + tid * ept;
+          double v0 = 0.0, v1 = 0.0;
+          if (t0 < kk) v0 = (double)prob_of(__ldg(nb_row + t0) + off);
+          if (ept == 2 && t0 + 1 < kk) v1 = (double)prob_of(__ldg(nb_row + t0 + 1) + off);
           double total;
-          const double incl = carry + block_scan_incl(v, S.dscr, &total);
-          const float cs = (float)(incl * (double)scale);
-          const bool ok = (tt >= kk) || (cs <= bound);   // sums are non-decreasing: ok is a prefix of the chunk
-          S.csv[tid] = cs;
-          const unsigned bal = __ballot_sync(0xffffffffu, ok);
-          if ((tid & 31) == 0 && bal != 0xffffffffu) atomicMin(&S.iscr[39], (tid & ~31) + __ffs(~bal) - 1);
+          const double incl1 = carry + block_scan_incl(v0 + v1, S.dscr, &total);   // prefix through the thread's last neighbour
+          const float cs0 = (float)((incl1 - v1) * (double)scale);
+          const float cs1 = (float)(incl1 * (double)scale);
+          int fail = 0x7fffffff;                         // sums are non-decreasing: the failures form a suffix
+          if (t0 < kk && !(cs0 <= bound)) fail = tid * ept;
+          else if (ept == 2 && t0 + 1 < kk && !(cs1 <= bound)) fail = tid * ept + 1;
+          S.csv[tid * ept] = cs0;
+          if (ept == 2) S.csv[tid * ept + 1] = cs1;
+          const int wfail = __reduce_min_sync(0xffffffffu, fail);
+          if ((tid & 31) == 0 && wfail != 0x7fffffff) atomicMin(&S.iscr[39], wfail);
           __syncthreads();
           const int cnt = S.iscr[39];
           if (cnt > 0) S.fscr[35] = S.csv[cnt - 1];      // every thread stores the same value

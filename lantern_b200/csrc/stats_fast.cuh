@@ -151,17 +151,27 @@ __global__ void __launch_bounds__(NT, (NT <= 512 ? 2 : 1)) row_stats_fast_kernel
         const float lo = mean + (z_run - win_run) * sd, hi = mean + (z_run + win_run) * sd;
         if (lo < hi) {
           // bracket pass: count elements above hi, park the elements inside [lo, hi] in the thread's column
-          int above = 0, slot = 0;
+          // Branch-free, five instructions per element: two compares, a predicated store through a running shared
+          // address (the thread's parking column), its predicated advance, and the predicated count of elements above.
+          int above = 0;
+          const uint32_t park0 = smem_u32(park + tid);
+          uint32_t paddr = park0;
 #pragma unroll
           for (int e = 0; e < NE; ++e) {
-            const float v = s[e];
-            const bool ab = v > hi;
-            above += ab;
-            if (!ab && v >= lo) {
-              park[slot * NT + tid] = v;
-              ++slot;
-            }
+            asm volatile(
+                "{\n"
+                ".reg .pred pa, pin;\n"
+                "setp.gt.f32 pa, %2, %4;\n"
+                "setp.ge.and.f32 pin, %2, %3, !pa;\n"
+                "@pin st.shared.f32 [%0], %2;\n"
+                "@pin add.u32 %0, %0, %5;\n"
+                "@pa add.s32 %1, %1, 1;\n"
+                "}\n"
+                : "+r"(paddr), "+r"(above)
+                : "f"(s[e]), "f"(lo), "f"(hi), "n"(NT * 4)
+                : "memory");
           }
+          const int slot = (int)((paddr - park0) / (NT * 4));
           const int wa = __reduce_add_sync(0xffffffffu, above), wi = __reduce_add_sync(0xffffffffu, slot);
           if (lane == 0) fs.cnt_part[warp] = (unsigned)wa | ((unsigned)wi << 16);
           __syncthreads();   // B2

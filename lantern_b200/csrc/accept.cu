@@ -597,6 +597,9 @@ __global__ void __launch_bounds__(LNE > 0 ? kLazyThreads : kWalkThreads) walk_ke
         break;
       }
       // ---------------- rejection: residual distribution ----------------
+      // every thread must have read this candidate's probabilities (px, first prefix sum) before any entry is zeroed:
+      // the shortcuts above can reach this point without passing a barrier
+      __syncthreads();
       const bool zero_nb = cfg.lantern && relaxable && idx != -1;
       if (cfg.static_tree) {
         const float* q = P.in.draft_op + ((size_t)b * cfg.n_q_rows + P.in.node_qrow[cnode]) * (size_t)V;

@@ -98,12 +98,13 @@ __global__ void __launch_bounds__(kTreeThreads) dyntree_kernel(const DynTreePara
     haschild[pn] = 1;   // benign race: all writers store 1
   }
   __syncthreads();
-  // ---- depths: parents precede children, so ceil(log)-free relaxation rounds converge in max_depth rounds ----
-  for (int round = 0; round < DM; ++round) {
-    for (int i = tid + 1; i < T; i += kTreeThreads)
-      if (dep[i] < 0 && dep[par[i]] >= 0) dep[i] = dep[par[i]] + 1;
-    __syncthreads();
+  // ---- depths: every node walks its own parent chain (at most d_max steps; no shared writes but its own slot) ----
+  for (int i = tid + 1; i < T; i += kTreeThreads) {
+    int d = 0, a = i;
+    while (a > 0 && d <= T) { a = par[a]; ++d; }
+    dep[i] = d;
   }
+  __syncthreads();
   for (int i = tid; i < T; i += kTreeThreads) {
     P.parent[(size_t)b * T + i] = par[i];
     P.depth[(size_t)b * T + i] = dep[i];

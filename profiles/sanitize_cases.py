@@ -35,7 +35,7 @@ def accept(params, phases=3):
 
 def main():
     torch.cuda.set_device(0)
-    which = sys.argv[1:] or ["accept", "neighbors", "kv"]
+    which = sys.argv[1:] or ["accept", "neighbors", "kv", "greedy", "drafter", "session"]
     if "accept" in which:
         accept(dict(family="llamagen", ncols=2048, top_k=300, lantern_k=100, boost=11.0))            # generic statistics kernel
         accept(dict(family="lumina_mgpt", ncols=2048, top_k=500, lantern_k=100, depth=5))            # fast (TMA) statistics kernel
@@ -62,5 +62,57 @@ def main():
         print("kv ok", flush=True)
 
 
+def extra(which):
+    from lantern_b200 import draft_sample, dyntree, synth, verify
+    if "greedy" in which:
+        for lantern in (False, True):
+            b = C.build(dict(family="anole", ncols=1024, top_k=0, temperature=0.0, lantern=lantern, lantern_k=100,
+                             lantern_delta=0.2, boost=9.0, seed=86000))
+            best, a, row, _ = C.oracle_greedy(b)
+            fam = R.family_spec(b)
+            v = verify.Verifier(fam, cfg_scale=b.params["cfg_scale"], lantern=lantern, lantern_k=100, lantern_delta=0.2,
+                                nbr_table=None if b.table is None else torch.from_numpy(b.table.astype(np.int32)).cuda())
+            res = v.greedy(torch.from_numpy(b.cond)[None].cuda(), torch.from_numpy(b.uncond)[None].cuda(),
+                           torch.from_numpy(b.tree.tokens.astype(np.int32))[None].cuda(),
+                           torch.from_numpy(R.pad_retrieve([b.tree.retrieve_indices])).cuda())
+            torch.cuda.synchronize()
+            assert int(res.accept_length[0]) == a and int(res.best_candidate[0]) == best
+        print("greedy ok", flush=True)
+    if "drafter" in which:
+        e = synth.eagle2_expansion(70, depth=5, top_k=10, lo=4, hi=8196)
+        t = dyntree.build_dynamic_tree(torch.from_numpy(e.scores).cuda(), torch.from_numpy(e.tokens).cuda(),
+                                       torch.from_numpy(e.parents).cuda(), torch.tensor([e.sample_token]).cuda(), 58, top_k=10)
+        o = O.dynamic_tree(e.scores, e.tokens, e.parents, e.sample_token, 58, 10)
+        assert np.array_equal(t.reference_outputs(0)[1].cpu().numpy(), o[4])
+        logits = torch.randn(6, 4096, device="cuda") * 2.5
+        proc = PO.prepare_logits_processor(temperature=1.0, top_p=1.0, top_k=300)
+        idx, cond, probs = draft_sample.sample(logits, proc, 10, seed=3, step=4)
+        torch.cuda.synchronize()
+        oi, oc, op = O.draft_sample(logits[2].cpu().numpy(), O.Warp(1.0, 1.0, 300), 10, 3, 4, 2)
+        assert np.array_equal(idx[2].cpu().numpy(), oi)
+        print("drafter ok", flush=True)
+    if "session" in which:
+        from lantern_b200.session import HostSession
+        b = C.build(dict(family="lumina_mgpt", ncols=4096, top_k=500, lantern_k=100, depth=5, seed=87000))
+        o = C.oracle_step(b)
+        fam = R.family_spec(b)
+        v = verify.Verifier(fam, top_k=500, cfg_scale=b.params["cfg_scale"], lantern=True, lantern_k=100,
+                            lantern_delta=b.params["lantern_delta"], nbr_table=torch.from_numpy(b.table.astype(np.int32)).cuda())
+        ri = R.pad_retrieve([b.tree.retrieve_indices])
+        tok = b.tree.tokens.astype(np.int32)[None]
+        uni = b.uniforms.astype(np.float32)[None]
+        with HostSession(v, 1, b.tree.T, ri.shape[1], ri.shape[2], n_uniforms=uni.shape[1]) as sess:
+            for pin in (False, True):
+                cnd, unc = torch.from_numpy(b.cond)[None], torch.from_numpy(b.uncond)[None]
+                if pin:
+                    cnd, unc = cnd.pin_memory(), unc.pin_memory()
+                r = sess.step(cnd, unc, tok, ri, uniforms=uni)
+                assert r.in_place == pin
+                if o.margin >= 1e-5:
+                    assert int(r.accept_length[0]) == o.accept_length and int(r.token[0]) == o.token
+        print("session ok", flush=True)
+
+
 if __name__ == "__main__":
     main()
+    extra(sys.argv[1:] or ["greedy", "drafter", "session"])

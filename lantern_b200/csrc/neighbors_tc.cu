@@ -320,12 +320,30 @@ __global__ void __launch_bounds__(kSelThreads) nbr_select_kernel(const float* __
   const float cut = -kth + 2.0f * eps;
   if (tid == 0) { n_cand = 0; bad = 0; }
   __syncthreads();
+  {   // one shared atomic per warp: the thread counts its candidates, the warp reserves a range, lanes fill their slices
+    int mine = 0;
 #pragma unroll
-  for (int e = 0; e < NE; ++e) {
-    const int j = ((e >> 2) * kSelThreads + tid) * 4 + (e & 3);
-    if (j < N && j != r && -v[e] <= cut) {
-      const int p = atomicAdd(&n_cand, 1);
-      if (p < kCandMax) cidx[p] = j;
+    for (int e = 0; e < NE; ++e) {
+      const int j = ((e >> 2) * kSelThreads + tid) * 4 + (e & 3);
+      mine += (j < N && j != r && -v[e] <= cut) ? 1 : 0;
+    }
+    const int lane = tid & 31;
+    int incl = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += t;
+    }
+    int base = 0;
+    if (lane == 31) base = atomicAdd(&n_cand, incl);
+    int p = __shfl_sync(0xffffffffu, base, 31) + incl - mine;
+#pragma unroll
+    for (int e = 0; e < NE; ++e) {
+      const int j = ((e >> 2) * kSelThreads + tid) * 4 + (e & 3);
+      if (j < N && j != r && -v[e] <= cut) {
+        if (p < kCandMax) cidx[p] = j;
+        ++p;
+      }
     }
   }
   __syncthreads();

@@ -87,7 +87,7 @@ class Verifier:
     def __init__(self, family: FamilySpec, *, temperature: float = 1.0, top_k: int = 0, top_p: float = 1.0,
                  cfg_scale: float = 1.0, lantern: bool = False, lantern_k: int = 1000, lantern_delta: float = 0.1,
                  nbr_table: Optional[torch.Tensor] = None, static_tree: Optional[StaticTree] = None,
-                 device: Optional[torch.device] = None, schedule: str = "streamed"):
+                 device: Optional[torch.device] = None, schedule: str = "auto"):
         self.lib = _abi.load()
         if schedule not in _SCHEDULES:
             raise ValueError(f"schedule must be one of {sorted(_SCHEDULES)}")

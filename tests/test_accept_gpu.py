@@ -204,6 +204,11 @@ def test_top_p(top_p, top_k, temp):
     ("anole", dict()),
     ("lumina_mgpt", dict(depth=5, newline_depth=1)),
     ("llamagen", dict(ncols=4096, static_tree="mc_sim_7b_63", lantern_k=10, lantern_delta=10.0, top_k=500, boost=8.5)),
+    ("lumina_mgpt", dict(ncols=2048, depth=5, top_k=400, static_tree="mc_sim_7b_63", lantern_k=10, lantern_delta=5.0,
+                         boost=8.0)),
+    ("anole", dict(ncols=2048, static_tree="mc_sim_7b_63_balanced", top_k=400, lantern_k=10, lantern_delta=10.0,
+                   boost=8.0)),
+    ("llamagen", dict(ncols=2048, lantern=False, top_k=300, boost=10.0)),
 ])
 def test_lazy_statistics_mode(family, kw):
     """phases = 6: no streamed statistics kernel; the walk computes the statistics of the rows it visits."""

@@ -321,3 +321,54 @@ def test_row_statistics_exact_on_non_gaussian_rows(dist, ncols, top_k):
     # formed with the same constant): allow 2^-24 * |max| * log2(e) on top of the 2e-6 of the exp itself
     tol = 2e-6 + 1.0e-7 * 1.45 * np.abs(s.max(axis=1))
     assert np.all(np.abs(stats[:, 2] - want) / want < tol)
+
+
+def _random_params(rng):
+    family = rng.choice(["llamagen", "anole", "lumina_mgpt"])
+    ncols = int(rng.choice([1024, 2048, 4096]))
+    p = dict(family=family, ncols=ncols, depth=5 if family == "lumina_mgpt" else int(rng.choice([3, 4])),
+             total_tokens=int(rng.choice([12, 26, 59, 90])), tree=str(rng.choice(["eagle2", "random"])),
+             top_k=int(rng.choice([0, 50, 300, ncols // 4])), temperature=float(rng.choice([1.0, 0.7, 1.4])),
+             lantern=bool(rng.random() < 0.8), lantern_k=int(rng.choice([5, 64, 1000])),
+             lantern_delta=float(rng.choice([0.05, 0.1, 0.4, 1.5, 5.0])), cfg_scale=float(rng.choice([1.5, 3.0, 7.5])),
+             boost=float(rng.choice([8.0, 10.0, 12.0])))
+    if family == "lumina_mgpt":
+        p["temperature"] = 1.0                      # the reference applies no HF warper inside Lumina's walk
+        p["top_k"] = max(p["top_k"], 50)
+        p["newline_depth"] = int(rng.choice([-1, -1, 1, 2]))
+    elif rng.random() < 0.25:
+        p["top_p"] = float(rng.choice([0.9, 0.6]))
+    if rng.random() < 0.3:
+        p["static_tree"] = str(rng.choice(["mc_sim_7b_63", "medusa_2_7b_63", "reverse_balanced_25", "chain"]))
+        p["lantern_delta"] = float(rng.choice([5.0, 10.0, 0.1]))
+        p["lantern_k"] = int(rng.choice([5, 10, 100]))
+    return p
+
+
+@pytest.mark.parametrize("chunk", range(6))
+def test_random_configurations_match_oracle(chunk):
+    """Differential fuzz: random family / window / warp knobs / relaxation / tree shape / CFG scale, three prompts per
+    configuration, every schedule the configuration is eligible for; each prompt must equal its own oracle."""
+    rng = np.random.default_rng(9000 + chunk)
+    done = 0
+    while done < 7:
+        p = _random_params(rng)
+        built, orcs, seed, tries = [], [], int(rng.integers(1, 10**6)), 0
+        while len(built) < 3 and tries < 12:
+            tries += 1
+            b = C.build(dict(p, seed=seed + tries))
+            o = C.oracle_step(b)
+            if o.margin >= MARGIN:
+                built.append(b)
+                orcs.append(o)
+        if len(built) < 3:
+            continue
+        done += 1
+        lazy_ok = p["ncols"] in (2048, 4096) and not (1e-8 <= p.get("top_p", 1.0) < 1.0)
+        for phases in (3, 8) + ((6,) if lazy_ok else ()):
+            res = R.run_cases(built, phases=phases)
+            for i, o in enumerate(orcs):
+                try:
+                    R.compare(res, i, o)
+                except AssertionError as e:
+                    raise AssertionError(f"params={p} seed={built[i].params['seed']} phases={phases}: {e}") from e

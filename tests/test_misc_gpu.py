@@ -152,6 +152,20 @@ def test_host_session_python_api():
         pinned = sess.step(torch.from_numpy(cond).pin_memory(), torch.from_numpy(uncond).pin_memory(), tokens, ri,
                            uniforms=uni, want_sample_p=True)
     assert not staged.in_place and pinned.in_place
+    # the caller refills the same page-locked buffers every step: in-place reads must see the new contents (no stale
+    # device-side caching of host memory across steps).  Rotate the prompts inside the same pinned tensors.
+    pc, pu = torch.from_numpy(cond).pin_memory(), torch.from_numpy(uncond).pin_memory()
+    with HostSession(ver, len(built), b0.tree.T, ri.shape[1], ri.shape[2], n_uniforms=uni.shape[1]) as sess2:
+        first = sess2.step(pc, pu, tokens, ri, uniforms=uni)
+        perm = [1, 2, 3, 0]
+        pc.copy_(torch.from_numpy(cond[perm]))
+        pu.copy_(torch.from_numpy(uncond[perm]))
+        again = sess2.step(pc, pu, np.ascontiguousarray(tokens[perm]), np.ascontiguousarray(ri[perm]),
+                           uniforms=np.ascontiguousarray(uni[perm]))
+    assert first.in_place and again.in_place
+    for i, src in enumerate(perm):
+        assert int(again.accept_length[i]) == orcs[src].accept_length and int(again.token[i]) == orcs[src].token
+        assert int(first.accept_length[i]) == orcs[i].accept_length and int(first.token[i]) == orcs[i].token
     for r in (staged, pinned):
         for i, o in enumerate(orcs):
             assert int(r.accept_length[i]) == o.accept_length and int(r.token[i]) == o.token

@@ -174,7 +174,20 @@ __global__ void __launch_bounds__(NT, (NT <= 512 ? 2 : 1)) row_stats_fast_kernel
           const int slot = (int)((paddr - park0) / (NT * 4));
           const int wa = __reduce_add_sync(0xffffffffu, above), wi = __reduce_add_sync(0xffffffffu, slot);
           if (lane == 0) fs.cnt_part[warp] = (unsigned)wa | ((unsigned)wi << 16);
-          __syncthreads();   // B2
+          // the histogram of the parked elements is filled before the counts are known (it is only wasted on the rare
+          // rows whose bracket misses): one barrier covers both exchanges
+          const Classifier64 cls = make_classifier64(lo, hi);
+          unsigned fl0 = 0u, fl1 = 0u;   // fields of the first ten parked elements, six bits each
+#pragma unroll
+          for (int i = 0; i < 10; ++i) {
+            if (i < slot) {
+              const unsigned f = cls(park[i * NT + tid]);
+              if (i < 5) fl0 |= f << (6 * i); else fl1 |= f << (6 * (i - 5));
+              atomicAdd(&fs.hist[f], 1u);
+            }
+          }
+          for (int i = 10; i < slot; ++i) atomicAdd(&fs.hist[cls(park[i * NT + tid])], 1u);
+          __syncthreads();   // B2 + B3
           int tot_above = 0, tot_in = 0;
 #pragma unroll
           for (int w = 0; w < NW; ++w) {
@@ -185,19 +198,6 @@ __global__ void __launch_bounds__(NT, (NT <= 512 ? 2 : 1)) row_stats_fast_kernel
           const int k = cfg.top_k;
           if (tot_above < k && k <= tot_above + tot_in) {
             const int krem = k - tot_above;
-            const Classifier64 cls = make_classifier64(lo, hi);
-            // field of every parked element, six bits each (recomputed for elements past the tenth)
-            unsigned fl0 = 0u, fl1 = 0u;   // fields of the first ten parked elements, six bits each
-#pragma unroll
-            for (int i = 0; i < 10; ++i) {
-              if (i < slot) {
-                const unsigned f = cls(park[i * NT + tid]);
-                if (i < 5) fl0 |= f << (6 * i); else fl1 |= f << (6 * (i - 5));
-                atomicAdd(&fs.hist[f], 1u);
-              }
-            }
-            for (int i = 10; i < slot; ++i) atomicAdd(&fs.hist[cls(park[i * NT + tid])], 1u);
-            __syncthreads();   // B3
             // every warp scans the 64 fields itself: lane l owns fields 2l, 2l+1
             const unsigned c0 = fs.hist[2 * lane], c1 = fs.hist[2 * lane + 1];
             unsigned incl = c0 + c1;

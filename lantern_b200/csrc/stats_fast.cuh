@@ -6,7 +6,7 @@
 //     does the arithmetic of the current row;
 //   * the row lives in registers (NE values per thread); CFG mix + temperature are applied while lifting;
 //   * every block-wide exchange is "warp partials -> shared memory -> one barrier -> every warp combines the
-//     partials itself": six barriers per row (statistics, bracket counts, histogram, compaction, rank, sum);
+//     partials itself": five barriers per row (statistics, bracket counts + histogram, compaction, rank, sum);
 //   * the exact top-k threshold comes from the tier-1 bracket select of select.cuh restated in that style; if the
 //     bracket misses (or the row is not finite) the tier-2/3 selectors of select.cuh finish the row.
 //

@@ -32,7 +32,7 @@ struct FastSmem {
 };
 
 template <int DT, int NT, int NQ, int MODE>   // MODE 1: cond + uncond, MODE 2: cond only
-__global__ void __launch_bounds__(NT, (NT <= 512 ? 2 : 1)) row_stats_fast_kernel(const AcceptParams P) {
+__global__ void __launch_bounds__(NT, (NT <= 256 ? 2 : 1)) row_stats_fast_kernel(const AcceptParams P) {
   constexpr int NE = NQ * 4, NW = NT / 32, EB = Elem<DT>::kBytes;
   __shared__ FastSmem<NW> fs;
   __shared__ SelectSmem sm;   // slow path only

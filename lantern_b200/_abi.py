@@ -8,7 +8,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "liblantern_b200.so")
+# LANTERN_B200_LIB: path of an alternative build of the same ABI (A/B measurements of kernel variants)
+LIB_PATH = os.environ.get("LANTERN_B200_LIB") or os.path.join(_HERE, "liblantern_b200.so")
 
 F32, BF16, F16 = 0, 1, 2
 FAMILY_VANILLA, FAMILY_LLAMAGEN, FAMILY_ANOLE, FAMILY_LUMINA = 0, 1, 2, 3

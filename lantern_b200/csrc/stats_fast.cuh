@@ -75,9 +75,11 @@ __global__ void __launch_bounds__(NT, (NT <= 256 ? 2 : 1)) row_stats_fast_kernel
   // (item, t) of the current row and of the next row of this CTA, advanced without divisions
   int item = (int)blockIdx.x / cfg.n_rows, trow = (int)blockIdx.x % cfg.n_rows;
   int n_item = item, n_trow = trow;
+  const int step_item = (int)gridDim.x / cfg.n_rows, step_row = (int)gridDim.x % cfg.n_rows;
   auto advance = [&](int& it, int& tr) {
-    tr += (int)gridDim.x;
-    while (tr >= cfg.n_rows) { tr -= cfg.n_rows; ++it; }
+    tr += step_row;
+    it += step_item;
+    if (tr >= cfg.n_rows) { tr -= cfg.n_rows; ++it; }
   };
   advance(n_item, n_trow);
   if (tid == 0) {
@@ -178,8 +180,10 @@ __global__ void __launch_bounds__(NT, (NT <= 256 ? 2 : 1)) row_stats_fast_kernel
           // rows whose bracket misses): one barrier covers both exchanges
           const Classifier64 cls = make_classifier64(lo, hi);
           unsigned fl0 = 0u, fl1 = 0u;   // fields of the first ten parked elements, six bits each
+          const int wmax = __reduce_max_sync(0xffffffffu, slot);   // warp-uniform trip count of the unrolled loops
 #pragma unroll
           for (int i = 0; i < 10; ++i) {
+            if (i >= wmax) break;
             if (i < slot) {
               const unsigned f = cls(park[i * NT + tid]);
               if (i < 5) fl0 |= f << (6 * i); else fl1 |= f << (6 * (i - 5));
@@ -218,6 +222,7 @@ __global__ void __launch_bounds__(NT, (NT <= 256 ? 2 : 1)) row_stats_fast_kernel
             if (cntF <= kListMax) {
 #pragma unroll
               for (int i = 0; i < 10; ++i) {
+                if (i >= wmax) break;
                 const unsigned f = ((i < 5 ? fl0 >> (6 * i) : fl1 >> (6 * (i - 5))) & 63u);
                 if (i < slot && f == F) fs.list[atomicAdd(&fs.list_n, 1)] = park[i * NT + tid];
               }
@@ -277,7 +282,9 @@ __global__ void __launch_bounds__(NT, (NT <= 256 ? 2 : 1)) row_stats_fast_kernel
 #pragma unroll
     for (int e = 0; e < NE; ++e) {
       const float ev = ex(s[e]);
-      part += (s[e] >= thr) ? ev : 0.f;
+      // predicated add (two instructions) instead of compare + select + add; adding 0.f is the identity, so the sum
+      // is bit-identical
+      asm("{\n.reg .pred pk;\nsetp.ge.f32 pk, %1, %2;\n@pk add.f32 %0, %0, %3;\n}\n" : "+f"(part) : "f"(s[e]), "f"(thr), "f"(ev));
     }
     part = warp_reduce(part, OpSum());
     if (lane == 0) fs.sum_part[warp] = part;

@@ -1007,6 +1007,7 @@ static void fill_params(AcceptParams& P, const lantern_accept_cfg* cfg, const la
   }
   P.win_sd_first = 0.25f;
   if (const char* w = getenv("LANTERN_WIN_SD")) P.win_sd = (float)atof(w);   // tuning knob (any value keeps the select exact)
+  P.inv_ncols = 1.0f / (float)cfg->ncols;
   P.tail_raw = cfg->family == LANTERN_FAMILY_VANILLA;
   P.lumina = cfg->family == LANTERN_FAMILY_LUMINA;
   P.static_zero_q = cfg->static_tree && cfg->family != LANTERN_FAMILY_LUMINA;

@@ -29,6 +29,7 @@ struct AcceptParams {
   int lumina;
   int static_zero_q;  // static + relaxed rejection zeroes neighbours in q (LlamaGen/Anole) instead of gtp
   int prefetch_rows;  // walk: pull the row of the child being tried towards L2 (off when the logits sit in host memory)
+  float inv_ncols;    // 1 / ncols
   float z_guess;      // inverse normal CDF of 1 - top_k/ncols: first bracket of the top-k select
   float win_sd;       // half-width of the bracket in standard deviations once a CTA tracks the observed quantile
   float win_sd_first; // half-width for a CTA's first row (Gaussian prior only)

@@ -17,6 +17,10 @@
 #include "accept_types.cuh"
 #include "select.cuh"
 
+#ifndef LANTERN_EXP
+#define LANTERN_EXP 0
+#endif
+
 namespace lantern {
 
 template <int NW>
@@ -131,11 +135,15 @@ __global__ void __launch_bounds__(NT, (NT <= 256 ? 2 : 1)) row_stats_fast_kernel
       if (tid == 0) P.stats[row] = st;
       continue;
     }
-    fsum = 0.f; fsq = 0.f; fmx = -INFINITY;
+    {   // lane l takes warp (l mod NW)'s partial; a butterfly over NW lanes leaves the totals in every lane
+      const float4 pw = fs.st_part[lane & (NW - 1)];
+      fsum = pw.x; fsq = pw.y; fmx = pw.w;
 #pragma unroll
-    for (int w = 0; w < NW; ++w) {
-      const float4 pw = fs.st_part[w];
-      fsum += pw.x; fsq += pw.y; fmx = fmaxf(fmx, pw.w);
+      for (int o = 1; o < NW; o <<= 1) {
+        fsum += __shfl_xor_sync(0xffffffffu, fsum, o);
+        fsq += __shfl_xor_sync(0xffffffffu, fsq, o);
+        fmx = fmaxf(fmx, __shfl_xor_sync(0xffffffffu, fmx, o));
+      }
     }
     const float m = fmx;
 
@@ -146,10 +154,13 @@ __global__ void __launch_bounds__(NT, (NT <= 256 ? 2 : 1)) row_stats_fast_kernel
       // a -inf / +inf / NaN element makes the sum of squares non-finite, a constant row has an empty bracket
       // (sd == 0): both are left to the slow path below
       const bool finite = isfinite(fmx) && isfinite(fsq);
+      // moments once per row; they only steer the bracket (exactness comes from the counts), so the reciprocal
+      // square root may be the approximate one.  A constant row gives 0 * inf = NaN: empty bracket -> slow path.
+      const float mean = fsum * P.inv_ncols;
+      const float var = fmaxf(fmaf(fsq, P.inv_ncols, -mean * mean), 0.f);
+      const float inv_sd = rsqrtf(var);
+      const float sd = var * inv_sd;
       if (finite) {
-        const float inv_n = 1.0f / (float)cfg.ncols;
-        const float mean = fsum * inv_n;
-        const float sd = sqrtf(fmaxf(fsq * inv_n - mean * mean, 0.f));
         const float lo = mean + (z_run - win_run) * sd, hi = mean + (z_run + win_run) * sd;
         if (lo < hi) {
           // bracket pass: count elements above hi, park the elements inside [lo, hi] in the thread's column
@@ -178,7 +189,9 @@ __global__ void __launch_bounds__(NT, (NT <= 256 ? 2 : 1)) row_stats_fast_kernel
           if (lane == 0) fs.cnt_part[warp] = (unsigned)wa | ((unsigned)wi << 16);
           // the histogram of the parked elements is filled before the counts are known (it is only wasted on the rare
           // rows whose bracket misses): one barrier covers both exchanges
-          const Classifier64 cls = make_classifier64(lo, hi);
+          Classifier64 cls;   // any monotone classifier keeps the select exact: approximate reciprocal
+          cls.scale = __fdividef(61.0f, hi - lo);
+          cls.bias23 = fmaf(-lo, cls.scale, 1.0f) + 8388608.0f;
           unsigned fl0 = 0u, fl1 = 0u;   // fields of the first ten parked elements, six bits each
           const int wmax = __reduce_max_sync(0xffffffffu, slot);   // warp-uniform trip count of the unrolled loops
 #pragma unroll
@@ -192,13 +205,9 @@ __global__ void __launch_bounds__(NT, (NT <= 256 ? 2 : 1)) row_stats_fast_kernel
           }
           for (int i = 10; i < slot; ++i) atomicAdd(&fs.hist[cls(park[i * NT + tid])], 1u);
           __syncthreads();   // B2 + B3
-          int tot_above = 0, tot_in = 0;
-#pragma unroll
-          for (int w = 0; w < NW; ++w) {
-            const unsigned c = fs.cnt_part[w];
-            tot_above += (int)(c & 0xffffu);
-            tot_in += (int)(c >> 16);
-          }
+          // both 16-bit fields of the packed counts sum without carry (at most ncols <= 32768 elements per row)
+          const unsigned csum = __reduce_add_sync(0xffffffffu, lane < NW ? fs.cnt_part[lane] : 0u);
+          const int tot_above = (int)(csum & 0xffffu), tot_in = (int)(csum >> 16);
           const int k = cfg.top_k;
           if (tot_above < k && k <= tot_above + tot_in) {
             const int krem = k - tot_above;
@@ -263,10 +272,7 @@ __global__ void __launch_bounds__(NT, (NT <= 256 ? 2 : 1)) row_stats_fast_kernel
         __syncthreads();
       }
       {   // remember where the quantile really was (in standard deviations) for the next row
-        const float inv_n = 1.0f / (float)cfg.ncols;
-        const float mean = fsum * inv_n;
-        const float sd = sqrtf(fmaxf(fsq * inv_n - mean * mean, 0.f));
-        const float z_obs = (thr - mean) / sd;
+        const float z_obs = (thr - mean) * inv_sd;
         // bracket width: the width the sampling noise of the quantile calls for (P.win_sd) after a hit, doubled
         // after every consecutive miss (rows whose shape the Gaussian prior describes badly)
         if (isfinite(z_obs)) {

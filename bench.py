@@ -369,6 +369,11 @@ def run_b200(args):
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     results = []
     with ClockSampler(local) as clocks:
+        # A step is ~0.1 ms of GPU work, the same order as one host launch: park the GPU on a ~1 ms spin kernel before
+        # the first event so that the K launches are already queued when the timed region starts and host jitter (the
+        # clock sampler starting, a busy host after the CPU arm) cannot leak into a device-side measurement.  The
+        # spin itself is outside the two events.
+        torch.cuda._sleep(2_000_000)
         ev0.record()
         for i in range(args.steps):
             results.append(run(i))

@@ -285,8 +285,21 @@ def test_lumina_bf16_window_misaligned_for_16_bytes(dtype):
 def test_row_statistics_exact_on_non_gaussian_rows(dist, ncols, top_k):
     """The tracked-quantile bracket is a speed heuristic; the threshold must stay the exact k-th largest (ties kept)
     and the softmax statistics right for any row shape.  Reads the RowStats workspace of a phases=1 launch."""
+    _check_row_statistics(dist, ncols, top_k, B=5)
+
+
+@pytest.mark.parametrize("dist", ["gauss", "quantised", "mixed_rows"])
+@pytest.mark.parametrize("ncols,top_k", [(8192, 2000), (16384, 2000)])
+def test_row_statistics_exact_with_several_rows_per_cta(dist, ncols, top_k):
+    """Same check with 1320 rows on the 296 (or 148) persistent CTAs: every CTA streams four to nine rows, so the
+    pipelined bulk copies, the row advance and the bracket that tracks the previous row's quantile all take part
+    (rows of different shapes follow each other in `mixed_rows`)."""
+    _check_row_statistics(dist, ncols, top_k, B=40)
+
+
+def _check_row_statistics(dist, ncols, top_k, B):
     rng = np.random.default_rng(hash((dist, ncols)) % 2**32)
-    B, T = 5, 33
+    T = 33
     shape = (B, T, ncols)
     if dist == "gauss":
         x = rng.standard_normal(shape) * 2.5

@@ -126,3 +126,14 @@ def test_dropin_signatures_match_reference():
         assert mine[:len(required)] == required, (name, mine, required)
         pos = [mine.index(p) for p in theirs]                 # raises if a reference parameter is missing
         assert pos == sorted(pos), (name, mine, theirs)
+
+
+def test_missing_library_fails_loudly(tmp_path):
+    """No CPU fallback: with the library path pointing at nothing (``LANTERN_B200_LIB``) the binding raises."""
+    import subprocess
+    import sys
+    code = "from lantern_b200 import _abi; _abi.load()"
+    env = dict(os.environ, LANTERN_B200_LIB=str(tmp_path / "absent.so"), PYTHONPATH=ROOT)
+    r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
+    assert r.returncode != 0
+    assert "no CPU fallback" in r.stderr and "absent.so" in r.stderr

@@ -240,7 +240,8 @@ LANTERN_API int lantern_build_neighbors(const float* E_dev, int32_t N, int32_t d
  * cat(scores_list), tokens [n_cand] = cat(ss_token), parents [n_groups] = cat(parents_list) (parent flat id + 1 of
  * each group of `top_k` siblings, 0 = root).  Outputs: tree_tokens [B,T] (draft_tokens, root = sample token),
  * parent [B,T], depth [B,T] (tree_position_ids), mask [B,T,T] (tree_mask, optional), retrieve [B,T,d_max]
- * (retrieve_indices, -1 padded; valid block is counts[b] = {n_leaves, max_depth+1}); rows sorted like the reference
+ * (retrieve_indices, -1 padded; valid block is counts[b] = {n_leaves, max_depth+1}; a tree deeper than d_max gives
+ * counts[b] = {-1, max_depth+1} and a truncated table); rows sorted like the reference
  * does when a logits processor is present if sort_rows != 0.  top-k tie rule: higher score, then lower flat index.
  */
 LANTERN_API int lantern_build_dynamic_tree(const float* scores_dev, const int32_t* tokens_dev, const int32_t* parents_dev,

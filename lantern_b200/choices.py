@@ -29,9 +29,37 @@ _PATHS: Dict[str, str] = {
 }
 
 NAMES = tuple(_PATHS)
+# BASELINE configs[2] asks for "tree sizes 10-80 nodes": beyond the six shipped shapes, `synth_<nodes>_<seed>` names a
+# deterministic random prefix-closed tree (children numbered consecutively, at most 10 per node, depth <= 5)
+SYNTH_NAMES = ("synth_10_1", "synth_24_2", "synth_40_3", "synth_80_4")
+
+
+def synth_tree(n_nodes: int, seed: int, max_depth: int = 5, max_children: int = 10) -> List[List[int]]:
+    state = (seed * 2654435761 + 12345) & 0xFFFFFFFF
+
+    def rnd(n: int) -> int:
+        nonlocal state
+        state = (state * 1664525 + 1013904223) & 0xFFFFFFFF
+        return (state >> 8) % n
+
+    paths: List[tuple] = [()]
+    kids = {(): 0}
+    while len(paths) - 1 < n_nodes:
+        open_ = [p for p in paths if len(p) < max_depth and kids[p] < max_children]
+        # favour first children (deep, narrow trees like the shipped ones): two draws, keep the parent with fewer kids
+        a, b = open_[rnd(len(open_))], open_[rnd(len(open_))]
+        par = a if kids[a] <= kids[b] else b
+        child = par + (kids[par],)
+        kids[par] += 1
+        kids[child] = 0
+        paths.append(child)
+    return [list(p) for p in paths[1:]]
 
 
 def tree(name: str) -> List[List[int]]:
+    if name.startswith("synth_"):
+        _, n, seed = name.split("_")
+        return synth_tree(int(n), int(seed))
     return [[int(c) for c in path] for path in _PATHS[name].split()]
 
 

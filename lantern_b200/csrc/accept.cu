@@ -265,8 +265,9 @@ __device__ __forceinline__ RowStats raw_row_stats(const AcceptParams& P, int b, 
 // Lazy mode (phases bit 2): statistics of a visited row computed inside the walk CTA, straight from the logits,
 // and the probability vector written from registers (one global read of the row instead of two, and no
 // statistics for the ~85 % of tree rows the walk never visits).  Same arithmetic as the streamed kernels.
+// Returns true (and writes nothing) when every live column is -inf: a pre-masked one-hot row (see set_distribution).
 template <int DT, int NE>
-__device__ __forceinline__ void lazy_probs(const AcceptParams& P, int b, int node, bool raw, float* p, float* park,
+__device__ __forceinline__ bool lazy_probs(const AcceptParams& P, int b, int node, bool raw, float* p, float* park,
                                            SelectSmem& sm, float* part_scr, float& z_run, float& win_run) {
   constexpr int NT = kLazyThreads, NW = NT / 32, NQ = NE / 4;
   const lantern_accept_cfg& cfg = P.cfg;
@@ -299,6 +300,7 @@ __device__ __forceinline__ void lazy_probs(const AcceptParams& P, int b, int nod
   for (int w = 0; w < NW; ++w) {
     fsum += sm.f4[0][w]; fsq += sm.f4[1][w]; fmn = fminf(fmn, sm.f4[2][w]); fmx = fmaxf(fmx, sm.f4[3][w]);
   }
+  if (fmx == -INFINITY) return true;   // block-uniform
   float thr = -INFINITY;
   if (P.do_topk && !raw) {
     bool found = false;
@@ -344,6 +346,7 @@ __device__ __forceinline__ void lazy_probs(const AcceptParams& P, int b, int nod
     o.w = s[q * 4 + 3] >= thr ? __fmul_rn(ex(s[q * 4 + 3]), inv) : 0.f;
     *reinterpret_cast<float4*>(p + e0) = o;
   }
+  return false;
 }
 
 template <int DT, bool VEC, int LNE>
@@ -413,6 +416,15 @@ __global__ void __launch_bounds__(LNE > 0 ? kLazyThreads : kWalkThreads) walk_ke
     return p_out;
   };
   int rows_read = 0;   // logits rows materialised into S.p (reported in the flags word; one-hot rows read nothing)
+  // CFG-mixed logit of one column of a tree row (any column of the vocabulary, not only the live window)
+  auto logit_at = [&](int node, int col) -> float {
+    const int64_t o = (int64_t)b * cfg.item_stride + (int64_t)node * cfg.row_stride + col;
+    const float c = Elem<DT>::load1(P.in.logits_cond, o);
+    const float u = P.mix.has_uncond ? Elem<DT>::load1(P.in.logits_uncond, o) : 0.f;
+    MixParams m = P.mix;
+    m.do_temp = 0;
+    return mix_temper(c, u, m);
+  };
   auto set_distribution = [&](int node, bool raw) {
     const long long row = (long long)b * T + node;
     RowStats st;
@@ -423,22 +435,38 @@ __global__ void __launch_bounds__(LNE > 0 ? kLazyThreads : kWalkThreads) walk_ke
     }
     __syncthreads();
     extra_tok = -1; p_extra = 0.f; p_out = 0.f; scale = 1.0f;
-    if (st.kind != LANTERN_ROW_IMAGE) {
-      for (int e = tid; e < ncols; e += NT) S.p[e] = 0.f;
-      extra_tok = st.kind == LANTERN_ROW_NEWLINE ? cfg.newline_token : cfg.eoi_token;
-      p_extra = 1.0f;
-      if (extra_tok >= col0 && extra_tok < col1) {   // degenerate configs: keep it inside the window
-        __syncthreads();
-        if (tid == 0) S.p[extra_tok - col0] = 1.0f;
-        extra_tok = -1; p_extra = 0.f;
+    int kind = st.kind;
+    if (kind == LANTERN_ROW_IMAGE) {
+      ++rows_read;
+      bool empty;
+      if (LNE > 0) {
+        empty = lazy_probs<DT, (LNE > 0 ? LNE : 4)>(P, b, node, raw, S.p, lazy_park, lazy_sm, lazy_part, z_run, win_run);
+      } else {
+        if (raw) st = raw_row_stats<DT, VEC>(P, b, node, S.fscr, S.dscr);
+        empty = st.mx == -INFINITY;
+        if (!empty) load_probs<DT, VEC>(P, b, node, st, S.p, raw);
       }
-    } else if (LNE > 0) {
-      ++rows_read;
-      lazy_probs<DT, (LNE > 0 ? LNE : 4)>(P, b, node, raw, S.p, lazy_park, lazy_sm, lazy_part, z_run, win_run);
-    } else {
-      ++rows_read;
-      if (raw) st = raw_row_stats<DT, VEC>(P, b, node, S.fscr, S.dscr);
-      load_probs<DT, VEC>(P, b, node, st, S.p, raw);
+      if (empty) {
+        // Every live column is -inf: the caller handed over rows that MultiModalLogitsProcessor already turned into
+        // one-hot newline / end-of-image rows (the reference's gathered [L, D, V] form, ea_model_lumina_mgpt.py:71-84,
+        // where no row_kinds travel).  The finite syntax column says which; an all -inf row keeps a zero window.
+        kind = -1;
+        if (cfg.eoi_token >= 0 && cfg.eoi_token < V && logit_at(node, cfg.eoi_token) > -INFINITY) kind = LANTERN_ROW_EOI;
+        else if (cfg.newline_token >= 0 && cfg.newline_token < V && logit_at(node, cfg.newline_token) > -INFINITY)
+          kind = LANTERN_ROW_NEWLINE;
+      }
+    }
+    if (kind != LANTERN_ROW_IMAGE) {
+      for (int e = tid; e < ncols; e += NT) S.p[e] = 0.f;
+      if (kind >= 0) {
+        extra_tok = kind == LANTERN_ROW_NEWLINE ? cfg.newline_token : cfg.eoi_token;
+        p_extra = 1.0f;
+        if (extra_tok >= col0 && extra_tok < col1) {   // degenerate configs: keep it inside the window
+          __syncthreads();
+          if (tid == 0) S.p[extra_tok - col0] = 1.0f;
+          extra_tok = -1; p_extra = 0.f;
+        }
+      }
     }
     __syncthreads();
   };
@@ -518,10 +546,12 @@ __global__ void __launch_bounds__(LNE > 0 ? kLazyThreads : kWalkThreads) walk_ke
       }
       const float r = uniform(draws++);
       float px = __fmul_rn(prob_of(x), scale);
-      bool relaxable = true;
+      // only image tokens own a neighbour-table row; anything else (masked to probability 0 by every family's
+      // tree_decoding) is tested on its own probability
+      bool relaxable = x >= col0 && x < col1;
       if (P.lumina) {
         if (is_syntax(x)) { px = 1.0f; relaxable = false; }
-        else if (!(x >= col0 && x < col1)) { px = 0.0f; relaxable = false; }
+        else if (!relaxable) px = 0.0f;
       }
       int idx = -1;
       const int* nb_row = nullptr;

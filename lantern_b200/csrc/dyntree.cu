@@ -137,7 +137,10 @@ __global__ void __launch_bounds__(kTreeThreads) dyntree_kernel(const DynTreePara
     const int rid = leaf_of[i];
     if (rid < 0) continue;
     int c = i;
-    for (int j = dep[i]; j >= 0; --j) { rows[rid * DM + j] = c; c = par[c]; }
+    for (int j = dep[i]; j >= 0; --j) {   // a tree deeper than d_max is reported through counts below, never written
+      if (j < DM) rows[rid * DM + j] = c;
+      c = par[c];
+    }
   }
   __syncthreads();
   // ---- lexicographic row order with padding last (cnets_llamagen.py:896-906) ----
@@ -147,7 +150,7 @@ __global__ void __launch_bounds__(kTreeThreads) dyntree_kernel(const DynTreePara
       for (int q = 0; q < nl; ++q) {
         if (q == r) continue;
         int cmp = 0;   // -1: q < r
-        for (int j = 0; j < D && cmp == 0; ++j) {
+        for (int j = 0; j < min(D, DM) && cmp == 0; ++j) {
           const int a = rows[q * DM + j] >= 0 ? rows[q * DM + j] : T + 5;
           const int bb = rows[r * DM + j] >= 0 ? rows[r * DM + j] : T + 5;
           cmp = a < bb ? -1 : (a > bb ? 1 : 0);
@@ -167,7 +170,8 @@ __global__ void __launch_bounds__(kTreeThreads) dyntree_kernel(const DynTreePara
     const int r = i / DM, j = i % DM;
     ri[rank[r] * DM + j] = rows[r * DM + j];
   }
-  if (tid == 0) { P.counts[b * 2] = nl; P.counts[b * 2 + 1] = D; }
+  // max_depth + 1 > d_max: the path table does not fit; n_leaves = -1 tells the caller (the rows above are truncated)
+  if (tid == 0) { P.counts[b * 2] = D <= DM ? nl : -1; P.counts[b * 2 + 1] = D; }
 }
 
 }  // namespace lantern

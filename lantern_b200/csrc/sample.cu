@@ -47,7 +47,7 @@ __global__ void tree_from_candidates_kernel(const int64_t* __restrict__ cand, co
   // tokens was zeroed by the memset the host enqueued before this launch
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     const int64_t node = ri[i];
-    ri32[i] = (int32_t)node;
+    ri32[i] = (node >= 0 && node < T) ? (int32_t)node : -1;   // out-of-range entries become padding (never indexed)
     if (node >= 0 && node < T) tokens[node] = (int32_t)cand[i];   // every path through a node carries the same token
   }
 }

@@ -29,6 +29,8 @@ class DynamicTree:
         """(draft_tokens [1,T] int64, retrieve_indices [L,D] int64, tree_mask [1,1,T,T] fp32, tree_position_ids [T])
         exactly as ``topK_genrate`` returns them; reads the two counts back (one small device->host copy)."""
         nl, D = (int(x) for x in self.counts[b].tolist())
+        if nl < 0:
+            raise ValueError(f"draft tree depth {D} exceeds d_max={self.retrieve.shape[2]}: rebuild with a larger d_max")
         return (self.tree_tokens[b:b + 1].long(), self.retrieve[b, :nl, :D].long(), self.mask[b][None, None],
                 self.depth[b].long())
 
@@ -66,9 +68,10 @@ def build_dynamic_tree(scores: torch.Tensor, tokens: torch.Tensor, parents: torc
 def from_drafter_lists(scores_list: Sequence[torch.Tensor], ss_token: Sequence[torch.Tensor],
                        parents_list: Sequence[torch.Tensor], sample_token: torch.Tensor, total_tokens: int,
                        top_k: int = 10, sort_rows: bool = True) -> DynamicTree:
-    """Convenience for a patched ``topK_genrate``: takes the three python lists as the reference builds them."""
+    """Convenience for a patched ``topK_genrate``: takes the three python lists as the reference builds them.
+    ``scores_list`` holds one entry per drafted level, so the deepest leaf path has ``len(scores_list) + 1`` nodes."""
     scores = torch.cat([s.reshape(-1) for s in scores_list])
     tokens = torch.cat([t.reshape(-1) for t in ss_token])
     parents = torch.cat([p.reshape(-1) for p in parents_list])
     return build_dynamic_tree(scores, tokens, parents, sample_token.reshape(-1)[:1], total_tokens, top_k,
-                              sort_rows=sort_rows)
+                              d_max=max(8, len(scores_list) + 1), sort_rows=sort_rows)

@@ -23,6 +23,7 @@ the reference's order and the module RNG is advanced by exactly the number of dr
 from __future__ import annotations
 
 import random
+import threading
 from dataclasses import dataclass
 from typing import List, Optional, Sequence, Tuple
 
@@ -130,6 +131,20 @@ def lumina_row_kinds(position_ids_plus1: torch.Tensor, image_start_idx: int, h: 
     return kinds
 
 
+def lumina_process_rows(rows: torch.Tensor, kinds: torch.Tensor, fam: FamilySpec, top_k: int) -> torch.Tensor:
+    """``MultiModalLogitsProcessor`` + ``InterleavedTopKLogitsWarper`` (ea_model_lumina_mgpt.py:45-112) on CFG-mixed
+    rows [T, V] - the unfused (``lantern_fused=False``) path of a stand-in that carries no processor objects."""
+    out = torch.full_like(rows, -float("inf"))
+    img = kinds == _abi.ROW_IMAGE
+    out[img, fam.col0:fam.col0 + fam.ncols] = rows[img, fam.col0:fam.col0 + fam.ncols]
+    out[kinds == _abi.ROW_NEWLINE, fam.newline_token] = 0
+    out[kinds == _abi.ROW_EOI, fam.eoi_token] = 0
+    if top_k > 0:
+        kth = torch.topk(out, min(top_k, out.shape[-1]))[0][..., -1, None]
+        out = out.masked_fill(out < kth, -float("inf"))
+    return out
+
+
 # ------------------------------------------------------------------------------------------------
 # Core marshalling
 # ------------------------------------------------------------------------------------------------
@@ -179,8 +194,10 @@ def _draw_python_uniforms(n: int):
 
 
 class _HostIO:
-    """Per-device staging for the batch-1 drop-in call: pinned host buffers for the uniforms going in and the five
-    result integers coming out, so that one call costs two async copies and a single stream synchronisation."""
+    """Staging for the batch-1 drop-in call, one per (device, host thread): pinned host buffers for the uniforms going
+    in and the five result integers coming out, so that one call costs two async copies and a single stream
+    synchronisation.  A call is synchronous, so a thread never has two calls in flight on one buffer; different
+    threads (one patched model each) get their own."""
 
     def __init__(self, device):
         self.u_host = torch.empty(4096, dtype=torch.float32).pin_memory()
@@ -194,7 +211,7 @@ _host_io = {}
 
 
 def _io(device) -> _HostIO:
-    key = str(device)
+    key = (str(device), threading.get_ident())
     io = _host_io.get(key)
     if io is None:
         io = _host_io[key] = _HostIO(device)
@@ -281,7 +298,10 @@ def _verify(fam: FamilySpec, logits, candidates: torch.Tensor, *, temp=1.0, top_
         if n_u > io.u_np.shape[0]:
             raise ValueError(f"tree of {T} nodes exceeds the uniform staging buffer")
         io.u_np[:T] = u                                   # float64 -> float32, round to nearest like torch
-        io.u_np[T] = float(torch.rand(()).item())         # bonus-token draw comes from torch's generator
+        # The bonus-token draw comes from torch's CPU generator.  The reference's torch.multinomial advances the CUDA
+        # generator instead (by an amount that is an implementation detail of ATen), so after a seeded run the torch RNG
+        # states differ; the python `random` stream - the one that decides acceptance - is replayed exactly.
+        io.u_np[T] = float(torch.rand(()).item())
         uniforms = io.u_dev[:n_u].view(1, n_u)
         uniforms.copy_(io.u_host[:n_u].view(1, n_u), non_blocking=True)
     res = ver.step(cond, uncond, tokens, retrieve, row_kinds=kinds, uniforms=uniforms,
@@ -570,10 +590,21 @@ class LuminaVerifyMixin:
         fam = verify.LUMINA
         return fam if fam.vocab == vocab else fam.resized(getattr(self, "lantern_image_tokens", fam.ncols), vocab)
 
+    def _image_top_k(self) -> int:
+        """The k of the InterleavedTopKLogitsWarper the reference applies in tree_decoding: ``generate(top_k=...)``
+        appends it to ``self.internal_logits_processors`` on every call (ea_model_lumina_mgpt.py:822-823) and
+        tree_decoding reads entry [1] (:605).  ``lantern_image_top_k`` is only the fallback for stand-ins that carry
+        no processor list."""
+        procs = getattr(self, "internal_logits_processors", None)
+        if procs is not None and len(procs) > 1 and hasattr(procs[1], "image_top_k"):
+            return int(procs[1].image_top_k)
+        return int(self.lantern_image_top_k)
+
     def tree_decoding(self, tree_candidates, attention_mask, past_key_values, tree_position_ids, input_ids,
                       retrieve_indices):
         """ea_model_lumina_mgpt.py:556-608: both CFG modes run the caller's target model; the CFG mix, the
-        MultiModalLogitsProcessor row classes, the top-k and the gather are left to the fused kernel."""
+        MultiModalLogitsProcessor row classes, the top-k and the gather are left to the fused kernel
+        (``lantern_fused=False`` keeps the reference's own post-processing and returns the gathered [L, D, V])."""
         position_ids = tree_position_ids + input_ids.shape[1]
         if self.cfg_mode == "parallel":
             tc = torch.cat((tree_candidates, tree_candidates), dim=0)
@@ -588,9 +619,20 @@ class LuminaVerifyMixin:
             _, uncond_tree_logits, uncond_hidden_states = self(
                 input_ids=tree_candidates, output_orig=True, past_key_values=past_key_values["uncond"],
                 position_ids=position_ids - self.image_start_token_id_index)
+        top_k = self._image_top_k()
+        if not self.lantern_fused:
+            mixed = uncond_tree_logits + self.cfg_scale * (tree_logits - uncond_tree_logits)
+            procs = getattr(self, "internal_logits_processors", None)
+            if procs is not None and len(procs) > 1:       # the reference's own processors (:600-605)
+                rows = procs[0](mixed[0], image_start_token_id_index=self.image_start_token_id_index,
+                                position_ids=position_ids + 1)
+                rows = procs[1](rows)
+            else:
+                rows = lumina_process_rows(mixed[0], lumina_row_kinds(position_ids + 1, self.image_start_token_id_index),
+                                           self._family(mixed.shape[-1]), top_k)
+            return rows[retrieve_indices], hidden_states, uncond_hidden_states
         kinds = lumina_row_kinds(position_ids + 1, self.image_start_token_id_index)[None].contiguous()
-        handle = TreeLogits(tree_logits, uncond_tree_logits, float(self.cfg_scale), retrieve_indices, kinds,
-                            int(self.lantern_image_top_k))
+        handle = TreeLogits(tree_logits, uncond_tree_logits, float(self.cfg_scale), retrieve_indices, kinds, top_k)
         return handle, hidden_states, uncond_hidden_states
 
     def evaluate_posterior(self, logits, candidates, cart_candidates_prob=None, original_prob=None, p_indices=None,

@@ -46,7 +46,8 @@ class Built:
 def default_params(**kw) -> dict:
     p = dict(family="llamagen", ncols=None, tree="eagle2", total_tokens=59, depth=4, seed=0,
              lantern=True, lantern_k=1000, lantern_delta=0.1, temperature=1.0, top_k=2000, top_p=1.0,
-             cfg_scale=3.0, cfg=True, boost=13.0, static_tree=None, newline_depth=-1, sharp=1.0, table_seed=0)
+             cfg_scale=3.0, cfg=True, boost=13.0, static_tree=None, newline_depth=-1, sharp=1.0, table_seed=0,
+             newline_junk=False)
     p.update(kw)
     return p
 
@@ -98,7 +99,8 @@ def build(params: dict) -> Built:
             row_kinds[tree.depth == nd] = O.ROW_NEWLINE
             if static_name is None:
                 # children of newline rows: first child is the newline token, the rest are junk ids
-                seen = set()
+                # (newline_junk: every child is junk, so the walk rejects them all and ends on the one-hot row)
+                seen = set(range(T)) if p["newline_junk"] else set()
                 for i in range(1, T):
                     par = int(tree.parent[i])
                     if row_kinds[par] == O.ROW_NEWLINE:

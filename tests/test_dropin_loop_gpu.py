@@ -62,9 +62,10 @@ class _Model(PO.VerifyMixin):
         uncond = base + synth.gauss(self.calls, (T, V), stream=7) * np.float32(0.25)
         logits = torch.from_numpy(np.stack([cond, uncond])).to(self.dev)
         self.last_logits = (cond, uncond)
-        pos = position_ids.reshape(-1, T)[0]
-        # KV rows of the tree tokens: value = absolute position, so compaction is easy to check
-        self.kv[:, :, :, pos, :] = pos.to(torch.bfloat16)[None, None, None, :, None]
+        # KV rows of the tree tokens: node i is appended at slot len + i (the root's position id is len); value = slot,
+        # so compaction is easy to check
+        slots = int(position_ids.reshape(-1, T)[0, 0]) + torch.arange(T, device=self.dev)
+        self.kv[:, :, :, slots, :] = slots.to(torch.bfloat16)[None, None, None, :, None]
         hidden = torch.zeros(2, T, H, device=self.dev)
         return None, logits, hidden
 
@@ -99,6 +100,7 @@ def test_reference_style_loop_with_dropin_methods():
                           np.asarray(u + [0.5]), fam, O.Warp(1.0, 1.0, 500), True, 100, 0.1, m.nearest_latents)
         if o.margin >= 1e-5:
             assert int(best) == o.best_candidate and a == o.accept_length
+        retrieve_prev = retrieve_indices
         out = m.update_inference_inputs(input_ids, candidates, best, a, retrieve_indices, proc, new_token, [m.kv], cur_len,
                                         hidden, sample_p, 3.0)
         input_ids, draft_tokens, retrieve_indices, tree_mask, tree_pos, new_token, _, token = out
@@ -107,6 +109,7 @@ def test_reference_style_loop_with_dropin_methods():
         assert input_ids.shape[1] == prev_len + a + 1
         assert int(cur_len[0]) == prev_len + a + 1
         kept = m.kv[0, 0, 0, prev_len:prev_len + a + 1, 0].float().cpu().numpy()
-        assert len(kept) == a + 1 and np.all(np.diff(kept) > 0) and kept[0] == prev_len    # accepted positions, in path order
+        sel_prev = retrieve_prev[int(best), :a + 1].cpu().numpy() + prev_len
+        assert kept.tolist() == [float(x) for x in sel_prev]                        # accepted slots, in path order
         assert token.shape == (1, 1) and 0 <= int(token) < V and float(sample_p[int(token)]) > 0
     assert new_token == input_ids.shape[1] - 17 and m.ea_layer.calls == n_steps + 1

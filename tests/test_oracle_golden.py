@@ -61,7 +61,7 @@ def test_oracle_greedy_matches_reference(case):
     assert float(np.maximum(row.astype(np.float64), -1e30).sum()) == pytest.approx(case["row_sum"], rel=1e-12)
 
 
-@pytest.mark.parametrize("name", CH.NAMES)
+@pytest.mark.parametrize("name", CH.NAMES + CH.SYNTH_NAMES)
 def test_tree_buffers_match_reference(name):
     ref = TREES[name]
     tb = O.generate_tree_buffers(CH.tree(name))

@@ -138,7 +138,7 @@ def test_mixin_matches_reference_decisions(case, fused):
         if orc.margin >= 1e-5:
             break
     else:
-        pytest.skip("fragile decision margin for six different uniform streams")
+        pytest.fail("decision margin below 1e-5 for six different uniform streams: not a numerical accident")
     assert isinstance(best, torch.Tensor) and best.dim() == 0 and best.dtype == torch.int64 and best.device.type == "cpu"
     assert isinstance(a, int)
     assert int(best) == orc.best_candidate and a == orc.accept_length

@@ -13,7 +13,7 @@ with open(os.path.join(HERE, "golden", "tree_buffers.json")) as f:
     TREES = json.load(f)
 
 
-@pytest.mark.parametrize("name", CH.NAMES)
+@pytest.mark.parametrize("name", CH.NAMES + CH.SYNTH_NAMES)
 def test_generate_tree_buffers_matches_reference(name):
     ref = TREES[name]
     tb = trees.generate_tree_buffers(CH.tree(name), device="cpu")
@@ -26,7 +26,7 @@ def test_generate_tree_buffers_matches_reference(name):
     assert got_b == ref["b_indices"]
 
 
-@pytest.mark.parametrize("name", CH.NAMES)
+@pytest.mark.parametrize("name", CH.NAMES + CH.SYNTH_NAMES)
 def test_static_tree_csr(name):
     tb = trees.generate_tree_buffers(CH.tree(name), device="cpu")
     st = tb["static_tree"]

@@ -24,6 +24,7 @@
 #include "accept_types.cuh"
 #include "select.cuh"
 #include "stats_fast.cuh"
+#include "stats_stream.cuh"
 #include "topp.cuh"
 
 namespace lantern {
@@ -856,7 +857,12 @@ static int launch_all(const AcceptParams& P_in, cudaStream_t stream, int phases)
   }
   const int mode = full ? (P.mix.has_uncond ? 1 : 2) : 0;
   const size_t stage_bytes = mode ? (((size_t)c.ncols * EB + 32 + 127) & ~size_t(127)) : 0;
-  const size_t park_bytes = (size_t)nq_inst * 4 * nt * sizeof(float) + (mode == 1 ? 2 : (mode == 2 ? 1 : 0)) * stage_bytes;
+  // streaming form (stats_stream.cuh): NT main threads + one select warp; LANTERN_STATS_OLD=1 keeps the round-1 kernel
+  const bool use_stream = mode && nt <= 512 && c.ncols <= 16384 && !getenv("LANTERN_STATS_OLD");
+  const int ps_slots = std::min(nq_inst * 4, 20);
+  const size_t park_bytes = (use_stream ? (size_t)ps_slots * nt * sizeof(float) + 2 * (size_t)(nt / 32) * kSegCap * sizeof(float)
+                                    : (size_t)nq_inst * 4 * nt * sizeof(float)) +
+                            (mode == 1 ? 2 : (mode == 2 ? 1 : 0)) * stage_bytes;
   if (park_bytes + 6 * 1024 > 227 * 1024) {
     set_error("row statistics kernel needs %zu bytes of shared memory", park_bytes);
     return LANTERN_E_UNSUPPORTED;
@@ -878,9 +884,27 @@ static int launch_all(const AcceptParams& P_in, cudaStream_t stream, int phases)
       LANTERN_CUDA(cudaFuncSetAttribute(kk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)park_bytes)); \
     kk<<<grid, NT, park_bytes, stream>>>(P);                                                              \
   } while (0)
+#define LAUNCH_STREAM_MODE(NT, NQ, M, TT)                                                                  \
+  do {                                                                                                    \
+    auto kk = row_stats_stream_kernel<DT, NT, NQ, M, TT>;                                                 \
+    if (park_bytes > 48 * 1024)                                                                           \
+      LANTERN_CUDA(cudaFuncSetAttribute(kk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)park_bytes)); \
+    kk<<<grid, NT + 64, park_bytes, stream>>>(P);                                                        \
+  } while (0)
+#define LAUNCH_STREAM(NT, NQ)                                   \
+  do {                                                          \
+    if (mode == 1) {                                            \
+      if (P.mix.do_temp) LAUNCH_STREAM_MODE(NT, NQ, 1, true);   \
+      else LAUNCH_STREAM_MODE(NT, NQ, 1, false);                \
+    } else {                                                    \
+      if (P.mix.do_temp) LAUNCH_STREAM_MODE(NT, NQ, 2, true);   \
+      else LAUNCH_STREAM_MODE(NT, NQ, 2, false);                \
+    }                                                           \
+  } while (0)
 #define LAUNCH_FAST(NT, NQ)                     \
   do {                                          \
-    if (mode == 1) LAUNCH_FAST_MODE(NT, NQ, 1); \
+    if (use_stream) LAUNCH_STREAM(NT, NQ);      \
+    else if (mode == 1) LAUNCH_FAST_MODE(NT, NQ, 1); \
     else LAUNCH_FAST_MODE(NT, NQ, 2);           \
   } while (0)
   if (!(phases & 1) || (phases & 4)) {
@@ -909,6 +933,8 @@ static int launch_all(const AcceptParams& P_in, cudaStream_t stream, int phases)
     return LANTERN_E_UNSUPPORTED;
   }
 #undef LAUNCH_FAST
+#undef LAUNCH_STREAM
+#undef LAUNCH_STREAM_MODE
 #undef LAUNCH_FAST_MODE
 #undef LAUNCH_STATS
   LANTERN_CUDA(cudaGetLastError());
@@ -1035,9 +1061,15 @@ static void fill_params(AcceptParams& P, const lantern_accept_cfg* cfg, const la
     const double w = 2.9 * 1.4142135623730951 * sqrt(pk * (1.0 - pk) / (double)cfg->ncols) / (pdf > 1e-6 ? pdf : 1e-6);
     P.win_sd = (float)(w < 0.02 ? 0.02 : (w > 0.2 ? 0.2 : w));
   }
-  P.win_sd_first = 0.25f;
   if (const char* w = getenv("LANTERN_WIN_SD")) P.win_sd = (float)atof(w);   // tuning knob (any value keeps the select exact)
+  // A CTA's first rows only have the Gaussian prior: twice the tracked width (the prior is exact for Gaussian rows, so
+  // the noise of one sample quantile is all that has to fit; a miss costs one exact redo and doubles the width, up to
+  // 0.25 sd).  Wider first brackets were measured slower: every parked element is work for one select warp.
+  P.win_sd_first = fminf(0.25f, 2.0f * P.win_sd);
+  if (const char* w = getenv("LANTERN_WIN_FIRST")) P.win_sd_first = (float)atof(w);
   P.inv_ncols = 1.0f / (float)cfg->ncols;
+  P.dbg = 0;
+  if (const char* d = getenv("LANTERN_STREAM_DBG")) P.dbg = atoi(d);
   P.tail_raw = cfg->family == LANTERN_FAMILY_VANILLA;
   P.lumina = cfg->family == LANTERN_FAMILY_LUMINA;
   P.static_zero_q = cfg->static_tree && cfg->family != LANTERN_FAMILY_LUMINA;

@@ -115,6 +115,9 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
                "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   asm volatile(
       "{\n"
@@ -191,6 +194,33 @@ __device__ __forceinline__ T block_reduce(T v, Op op, T identity, T* scratch) {
     if (lane == 0) scratch[32] = w;
   }
   __syncthreads();
+  return scratch[32];
+}
+
+// Thread groups the block-wide helpers below (and select.cuh) can be run by: the whole CTA, or the first N threads
+// of it behind a named barrier (the streaming row-statistics kernel keeps one warp out of its main group).
+struct BlockBar {
+  static __device__ __forceinline__ void sync() { __syncthreads(); }
+  static __device__ __forceinline__ int size() { return (int)blockDim.x; }
+};
+template <int ID, int N>
+struct NamedBar {
+  static __device__ __forceinline__ void sync() { asm volatile("bar.sync %0, %1;" ::"n"(ID), "n"(N) : "memory"); }
+  static __device__ __forceinline__ int size() { return N; }
+};
+template <class Bar, typename T, typename Op>
+__device__ __forceinline__ T group_reduce(T v, Op op, T identity, T* scratch) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = (Bar::size() + 31) >> 5;
+  v = warp_reduce(v, op);
+  Bar::sync();  // protect scratch from a previous use
+  if (lane == 0) scratch[warp] = v;
+  Bar::sync();
+  if (warp == 0) {
+    T w = lane < nwarp ? scratch[lane] : identity;
+    w = warp_reduce(w, op);
+    if (lane == 0) scratch[32] = w;
+  }
+  Bar::sync();
   return scratch[32];
 }
 

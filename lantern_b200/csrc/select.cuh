@@ -34,21 +34,21 @@ struct SelectSmem {
 };
 
 // MSB-first radix select on ordered keys (exact for any input); returns the k-th largest key.
-template <int NE>
+template <int NE, class Bar = BlockBar>
 __device__ __forceinline__ uint32_t radix_select_kth(const float (&s)[NE], int k, unsigned* hist /*[258]*/) {
   uint32_t prefix = 0, mask = 0;
   int krem = k;
   const int tid = threadIdx.x;
 #pragma unroll 1
   for (int shift = 24; shift >= 0; shift -= 8) {
-    for (int i = tid; i < 256; i += blockDim.x) hist[i] = 0;
-    __syncthreads();
+    for (int i = tid; i < 256; i += Bar::size()) hist[i] = 0;
+    Bar::sync();
 #pragma unroll
     for (int e = 0; e < NE; ++e) {
       const uint32_t key = float_key(s[e]);
       if ((key & mask) == prefix) atomicAdd(&hist[(key >> shift) & 0xffu], 1u);
     }
-    __syncthreads();
+    Bar::sync();
     if (tid < 32) {
       unsigned c[8], tot = 0;
 #pragma unroll
@@ -68,11 +68,11 @@ __device__ __forceinline__ uint32_t radix_select_kth(const float (&s)[NE], int k
         run += c[j];
       }
     }
-    __syncthreads();
+    Bar::sync();
     prefix |= hist[256] << shift;
     mask |= 0xffu << shift;
     krem -= (int)hist[257];
-    __syncthreads();
+    Bar::sync();
   }
   return prefix;
 }
@@ -96,7 +96,7 @@ __device__ __forceinline__ Classifier make_classifier(float lo, float hi) {
 
 // Block-wide count of the 16 fields.  On return sm.i_scr[1..3] = {field F holding the k-th largest element,
 // number of elements in higher fields, number of elements in F}.
-template <int NE>
+template <int NE, class Bar = BlockBar>
 __device__ __forceinline__ void count_fields(const float (&s)[NE], const Classifier& cls, int k, SelectSmem& sm) {
   static_assert(NE <= 255, "byte accumulators");
   // nibble-packed counters, flushed into byte accumulators every 15 elements
@@ -122,15 +122,15 @@ __device__ __forceinline__ void count_fields(const float (&s)[NE], const Classif
     const unsigned od = ((j < 4 ? o_lo : o_hi) >> ((j & 3) * 8)) & 0xffu;
     w[j] = ev | (od << 16);
   }
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = Bar::size() >> 5;
 #pragma unroll
   for (int j = 0; j < 8; ++j) w[j] = __reduce_add_sync(0xffffffffu, w[j]);   // 32 lanes * 255 < 65536: no carry
-  __syncthreads();   // previous readers of sm.total / warp_cnt are done
+  Bar::sync();   // previous readers of sm.total / warp_cnt are done
   if (lane == 0) {
 #pragma unroll
     for (int j = 0; j < 8; ++j) sm.warp_cnt[warp][j] = w[j];
   }
-  __syncthreads();
+  Bar::sync();
   if (threadIdx.x < 32) {
     const int f = threadIdx.x & 15;
     unsigned tot = 0;
@@ -147,12 +147,13 @@ __device__ __forceinline__ void count_fields(const float (&s)[NE], const Classif
       sm.i_scr[1] = f; sm.i_scr[2] = (int)above; sm.i_scr[3] = (int)tot;
     }
   }
-  __syncthreads();
+  Bar::sync();
 }
 
 // Exact krem-th largest (1-based) of sm.list[0..m): one warp per candidate, lanes split the comparisons.
+template <class Bar = BlockBar>
 __device__ __forceinline__ float rank_list(int m, int krem, SelectSmem& sm) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = Bar::size() >> 5;
   for (int i = warp; i < m; i += nwarp) {
     const float vi = sm.list[i];
     int gt = 0, ge = 0;
@@ -165,7 +166,7 @@ __device__ __forceinline__ float rank_list(int m, int krem, SelectSmem& sm) {
     ge = __reduce_add_sync(0xffffffffu, ge);
     if (lane == 0 && gt < krem && krem <= ge) sm.f_scr[0] = vi;   // every qualifying candidate has the same value
   }
-  __syncthreads();
+  Bar::sync();
   return sm.f_scr[0];
 }
 
@@ -266,7 +267,7 @@ __device__ __forceinline__ bool bracket_select(const float (&s)[NE], int k, floa
 
 // k-th largest of the row held in s[] (NE per thread, padded slots = -inf), 1 <= k <= number of slots.
 // Tier 2: starts from the full [row_min, row_max] range.  Returns false when it cannot converge (tier 3 needed).
-template <int NE>
+template <int NE, class Bar = BlockBar>
 __device__ __forceinline__ bool select_kth_largest(const float (&s)[NE], int k, float row_min, float row_max,
                                                 SelectSmem& sm, float* out) {
   const int tid = threadIdx.x;
@@ -279,7 +280,7 @@ __device__ __forceinline__ bool select_kth_largest(const float (&s)[NE], int k, 
   for (int it = 0; ok && !done && it < kSelMaxIters; ++it) {
     const Classifier cls = make_classifier(lo, hi);
     if (!isfinite(cls.scale) || !isfinite(cls.bias23)) { ok = false; break; }
-    count_fields<NE>(s, cls, k, sm);
+    count_fields<NE, Bar>(s, cls, k, sm);
     const int F = sm.i_scr[1];
     const unsigned above = (unsigned)sm.i_scr[2], cntF = (unsigned)sm.i_scr[3];
     const int krem = k - (int)above;   // rank inside field F (1-based from the top)
@@ -291,17 +292,17 @@ __device__ __forceinline__ bool select_kth_largest(const float (&s)[NE], int k, 
       if (NE > 32) {   // (not instantiated today; keeps the bitmask honest)
         hit = 0xffffffffu;
       }
-      __syncthreads();
+      Bar::sync();
       if (tid == 0) sm.i_scr[0] = 0;
-      __syncthreads();
+      Bar::sync();
       if (hit) {
 #pragma unroll
         for (int e = 0; e < NE; ++e) {
           if (cls(s[e]) == (unsigned)F) sm.list[atomicAdd(&sm.i_scr[0], 1)] = s[e];
         }
       }
-      __syncthreads();
-      result = rank_list((int)cntF, krem, sm);
+      Bar::sync();
+      result = rank_list<Bar>((int)cntF, krem, sm);
       done = true;
     } else {
       // ---- too many candidates: shrink the range to the exact [min, max] of field F and classify again ----
@@ -310,8 +311,8 @@ __device__ __forceinline__ bool select_kth_largest(const float (&s)[NE], int k, 
       for (int e = 0; e < NE; ++e) {
         if (cls(s[e]) == (unsigned)F) { mn = fminf(mn, s[e]); mxv = fmaxf(mxv, s[e]); }
       }
-      mn = -block_reduce(-mn, OpMaxF(), -INFINITY, sm.f4[0]);
-      mxv = block_reduce(mxv, OpMaxF(), -INFINITY, sm.f4[1]);
+      mn = -group_reduce<Bar>(-mn, OpMaxF(), -INFINITY, sm.f4[0]);
+      mxv = group_reduce<Bar>(mxv, OpMaxF(), -INFINITY, sm.f4[1]);
       if (mn == mxv) { result = mn; done = true; }
       else if (!isfinite(mn) || !isfinite(mxv)) { ok = false; }
       else { lo = mn; hi = mxv; }
@@ -322,12 +323,12 @@ __device__ __forceinline__ bool select_kth_largest(const float (&s)[NE], int k, 
 }
 
 // Tiers 2 + 3 behind one non-inlined call (rare path; works on the caller's copy of the row).
-template <int NE>
+template <int NE, class Bar = BlockBar>
 __device__ __noinline__ float select_slow(const float (&s)[NE], int k, float row_min, float row_max, SelectSmem& sm) {
   float r;
-  if (select_kth_largest<NE>(s, k, row_min, row_max, sm, &r)) return r;
-  __syncthreads();
-  return key_float(radix_select_kth<NE>(s, k, sm.hist));
+  if (select_kth_largest<NE, Bar>(s, k, row_min, row_max, sm, &r)) return r;
+  Bar::sync();
+  return key_float(radix_select_kth<NE, Bar>(s, k, sm.hist));
 }
 
 }  // namespace lantern

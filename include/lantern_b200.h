@@ -9,7 +9,8 @@
  *
  * Conventions
  *   - plain pointers and sizes only; all `*_dev` pointers are CUDA device pointers owned by
- *     the caller; nothing is allocated, cached or freed inside unless the call says so;
+ *     the caller; nothing is allocated, cached or freed inside (the host-buffer session and the
+ *     lantern_debug_* test hook say so where they do);
  *   - every launch goes to the caller's `stream` (a cudaStream_t passed as void*; NULL = legacy
  *     default stream); calls are asynchronous unless documented otherwise;
  *   - return value: 0 = LANTERN_OK, negative = LANTERN_E_*, positive = cudaError_t;
@@ -26,7 +27,7 @@
 extern "C" {
 #endif
 
-#define LANTERN_ABI_VERSION 1
+#define LANTERN_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define LANTERN_API __attribute__((visibility("default")))
@@ -227,12 +228,17 @@ LANTERN_API int lantern_kv_compact(const lantern_kv_cfg* cfg, void* const* slab_
 /*
  * Neighbour-table build (entrypoints/generate_codebook.py:53-60): for every codebook row the ids of
  * its K nearest other rows, nearest first; order = (squared L2 distance in fp64, id).
- * E_dev: [N, d] fp32 row-major.  out_dev: [N, K] int32.  Allocates and frees its own scratch (stream-ordered).
- * For K <= N/2 the candidates come from a tcgen05 distance GEMM and are re-ranked exactly; otherwise (or if the
- * GEMM's error bound is ever violated) every distance is computed in fp64.  Both routes give identical tables.
+ * E_dev: [N, d] fp32 row-major.  out_dev: [N, K] int32.  Caller-owned scratch of
+ * lantern_build_neighbors_workspace_bytes(N, d, K) bytes; nothing is allocated, no host synchronisation, every launch
+ * goes to `stream`.  For K <= N/2 (N <= 16384, d <= 256) the candidates come from a tcgen05 distance GEMM and are
+ * re-ranked exactly; rows that route cannot finish (candidate overflow on massive ties, a violated error bound) and all
+ * other shapes are computed entirely in fp64 by a second kernel.  Both routes give identical tables.
+ * route_dev (optional, device int32[2]): [0] = 1 when every row came from the tensor-core route, else 2;
+ * [1] = rows computed by the all-fp64 kernel.
  */
+LANTERN_API size_t lantern_build_neighbors_workspace_bytes(int32_t N, int32_t d, int32_t K);
 LANTERN_API int lantern_build_neighbors(const float* E_dev, int32_t N, int32_t d, int32_t K, int32_t* out_dev,
-                            void* stream);
+                                        void* workspace_dev, size_t workspace_bytes, int32_t* route_dev, void* stream);
 
 /*
  * Dynamic (EAGLE-2) draft-tree post-processing: the host loops at the end of the drafter's topK_genrate
@@ -267,10 +273,6 @@ LANTERN_API int lantern_draft_sample(const lantern_accept_cfg* cfg, const lanter
  * D~[i][j] = |e_i|^2 + |e_j|^2 - 2 e_i.e_j (tcgen05, TF32 cross term), fp32 [N, ld]. The diagonal holds
  * the computed value (~0); the select stage excludes self by index. */
 LANTERN_API int lantern_debug_dist_gemm(const float* E_dev, int32_t N, int32_t d, float* D_dev, int32_t ld, void* stream);
-
-/* Which route the last lantern_build_neighbors call on this thread took: 1 = tensor-core candidates + exact
- * re-rank, 2 = all-fp64 kernel (test hook). */
-LANTERN_API int lantern_debug_neighbors_path(void);
 
 /* Host-side copy of the device Philox stream (for tests and for seeding the CPU oracle):
  * draw i of item `item` at step `step`, i in [0, n). */

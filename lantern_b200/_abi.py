@@ -22,7 +22,7 @@ EXPORTS = (
     "lantern_version", "lantern_last_error", "lantern_accept_workspace_bytes", "lantern_accept_fused",
     "lantern_accept_phases",
     "lantern_sample_tokens", "lantern_kv_compact", "lantern_build_neighbors", "lantern_philox_uniforms",
-    "lantern_session_create", "lantern_session_step", "lantern_session_destroy", "lantern_debug_dist_gemm", "lantern_debug_neighbors_path", "lantern_build_dynamic_tree", "lantern_draft_sample",
+    "lantern_session_create", "lantern_session_step", "lantern_session_destroy", "lantern_debug_dist_gemm", "lantern_build_neighbors_workspace_bytes", "lantern_build_dynamic_tree", "lantern_draft_sample",
     "lantern_tree_from_candidates", "lantern_session_last_route", "lantern_accept_greedy",
     "lantern_accept_greedy_workspace_bytes",
 )
@@ -110,10 +110,12 @@ def load() -> C.CDLL:
     lib.lantern_kv_compact.restype = C.c_int
     lib.lantern_kv_compact.argtypes = [C.POINTER(KvCfg), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.lantern_build_neighbors.restype = C.c_int
-    lib.lantern_build_neighbors.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]
+    lib.lantern_build_neighbors.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
+                                            C.c_size_t, C.c_void_p, C.c_void_p]
+    lib.lantern_build_neighbors_workspace_bytes.restype = C.c_size_t
+    lib.lantern_build_neighbors_workspace_bytes.argtypes = [C.c_int32, C.c_int32, C.c_int32]
     lib.lantern_debug_dist_gemm.restype = C.c_int
     lib.lantern_debug_dist_gemm.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p]
-    lib.lantern_debug_neighbors_path.restype = C.c_int
     lib.lantern_draft_sample.restype = C.c_int
     lib.lantern_draft_sample.argtypes = [C.POINTER(AcceptCfg), C.POINTER(AcceptIn), C.c_int32, C.c_void_p, C.c_void_p,
                                          C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]

@@ -19,8 +19,13 @@ import torch
 from . import _abi
 
 
-def build_neighbor_table(embedding: torch.Tensor, k: Optional[int] = None) -> torch.Tensor:
-    """embedding: [N, d] codebook (``vq_model.quantize.embedding.weight``) -> int32 [N, K] on the same device."""
+_workspaces = {}
+
+
+def build_neighbor_table(embedding: torch.Tensor, k: Optional[int] = None, return_route: bool = False):
+    """embedding: [N, d] codebook (``vq_model.quantize.embedding.weight``) -> int32 [N, K] on the same device.
+    ``return_route``: also return the device int32[2] record (1 = tensor-core route for every row / 2 = some rows by the
+    all-fp64 kernel, and how many)."""
     lib = _abi.load()
     if embedding.dim() != 2:
         raise ValueError("embedding must be [N, d]")
@@ -30,9 +35,15 @@ def build_neighbor_table(embedding: torch.Tensor, k: Optional[int] = None) -> to
     N, d = E.shape
     K = N - 1 if k is None else int(k)
     out = torch.empty(N, K, dtype=torch.int32, device=E.device)
-    _abi.check(lib.lantern_build_neighbors(E.data_ptr(), N, d, K, out.data_ptr(),
-                                           torch.cuda.current_stream(E.device).cuda_stream))
-    return out
+    need = int(lib.lantern_build_neighbors_workspace_bytes(N, d, K))
+    key = str(E.device)
+    work = _workspaces.get(key)                      # caller-owned scratch, kept between calls (up to 1 GiB at N = 16384)
+    if work is None or work.numel() < need:
+        work = _workspaces[key] = torch.empty(max(need, 1), dtype=torch.uint8, device=E.device)
+    route = torch.zeros(2, dtype=torch.int32, device=E.device)
+    _abi.check(lib.lantern_build_neighbors(E.data_ptr(), N, d, K, out.data_ptr(), work.data_ptr(), work.numel(),
+                                           route.data_ptr(), torch.cuda.current_stream(E.device).cuda_stream))
+    return (out, route) if return_route else out
 
 
 def save_reference_format(table: torch.Tensor, save_path: str) -> str:

@@ -1068,8 +1068,6 @@ static void fill_params(AcceptParams& P, const lantern_accept_cfg* cfg, const la
   P.win_sd_first = fminf(0.25f, 2.0f * P.win_sd);
   if (const char* w = getenv("LANTERN_WIN_FIRST")) P.win_sd_first = (float)atof(w);
   P.inv_ncols = 1.0f / (float)cfg->ncols;
-  P.dbg = 0;
-  if (const char* d = getenv("LANTERN_STREAM_DBG")) P.dbg = atoi(d);
   P.tail_raw = cfg->family == LANTERN_FAMILY_VANILLA;
   P.lumina = cfg->family == LANTERN_FAMILY_LUMINA;
   P.static_zero_q = cfg->static_tree && cfg->family != LANTERN_FAMILY_LUMINA;

@@ -33,7 +33,6 @@ struct AcceptParams {
   float z_guess;      // inverse normal CDF of 1 - top_k/ncols: first bracket of the top-k select
   float win_sd;       // half-width of the bracket in standard deviations once a CTA tracks the observed quantile
   float win_sd_first; // half-width for a CTA's first row (Gaussian prior only)
-  int dbg;            // LANTERN_STREAM_DBG experiment switches (0 in production)
 };
 
 

@@ -148,6 +148,44 @@ __device__ __forceinline__ float mix_temper(float c, float u, const MixParams& m
   return v;
 }
 
+// Packed fp32 pairs (Blackwell FFMA2 / FADD2: one instruction, two lanes).  ptxas contracts a packed multiply feeding
+// a packed add into one FFMA2 whatever the rounding modifiers say, which would change the reference's separately
+// rounded CFG mix: mix_temper2 therefore keeps the multiply scalar.
+__device__ __forceinline__ uint64_t pack2(float a, float b) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ void unpack2(uint64_t p, float& a, float& b) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(p));
+}
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+// two elements of the CFG mix + temperature, bit-identical to mix_temper on each: c - u as fma(u, -1, c) (one rounding
+// of the exact difference), the scale as a scalar multiply, u + t as a packed add, the temperature as a scalar division
+__device__ __forceinline__ uint64_t mix_temper2(float c0, float c1, float u0, float u1, const MixParams& m) {
+  float v0 = c0, v1 = c1;
+  if (m.has_uncond) {
+    const uint64_t u = pack2(u0, u1);
+    float t0, t1;
+    unpack2(fma2(u, pack2(-1.0f, -1.0f), pack2(c0, c1)), t0, t1);
+    unpack2(add2(u, pack2(__fmul_rn(t0, m.cfg_scale), __fmul_rn(t1, m.cfg_scale))), v0, v1);
+  }
+  if (m.do_temp) {
+    v0 = __fdiv_rn(v0, m.temperature);
+    v1 = __fdiv_rn(v1, m.temperature);
+  }
+  return pack2(v0, v1);
+}
+
 // exp(s - m) for the softmax: one FFMA + MUFU.EX2.  The same function is used wherever a probability is formed
 // (row statistics, walk, tail), so numerator and denominator always agree; relative error <= ~3e-6 for
 // s - m >= -60 (2 ulp of ex2.approx plus the rounding of the scaled argument), inside the 1e-5 budget.

@@ -21,14 +21,17 @@ __global__ void transpose_kernel(const float* __restrict__ E, float* __restrict_
   }
 }
 
+// row_redo != NULL: only the rows the tensor-core route marked are computed (the others already hold their result).
 __global__ void __launch_bounds__(kNbrThreads) nbr_rows_kernel(const float* __restrict__ E,
                                                                const float* __restrict__ Et, int N, int d, int K,
-                                                               int NP /*pow2 >= N*/, int32_t* __restrict__ out) {
+                                                               int NP /*pow2 >= N*/, int32_t* __restrict__ out,
+                                                               const unsigned char* __restrict__ row_redo) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double* key = reinterpret_cast<double*>(smem_raw);
   int* idx = reinterpret_cast<int*>(smem_raw + (size_t)NP * 8);
   float* er = reinterpret_cast<float*>(smem_raw + (size_t)NP * 12);
   const int r = blockIdx.x, tid = threadIdx.x;
+  if (row_redo != nullptr && row_redo[r] == 0) return;
   for (int c = tid; c < d; c += kNbrThreads) er[c] = E[(int64_t)r * d + c];
   __syncthreads();
   for (int c = tid; c < NP; c += kNbrThreads) {
@@ -69,14 +72,31 @@ __global__ void __launch_bounds__(kNbrThreads) nbr_rows_kernel(const float* __re
 
 }  // namespace lantern
 
-static thread_local int g_last_path = 0;   // 1 = tensor-core candidates + exact re-rank, 2 = all-fp64 kernel
+bool neighbors_tc_eligible(int N, int d, int K);
+size_t neighbors_tc_workspace_bytes(int N, int d);
+int build_neighbors_tensor_core(const float* E_dev, int N, int d, int K, int32_t* out_dev, void* workspace,
+                                unsigned char** row_redo_out, int** flags_out, cudaStream_t s);
 
-extern "C" LANTERN_API int lantern_debug_neighbors_path(void) { return g_last_path; }
+// route_dev[0] = 1: every row came from the tensor-core route; 2: the exact kernel computed some (or all) rows;
+// route_dev[1] = rows the exact kernel computed.
+__global__ void nbr_route_kernel(const int* __restrict__ flags, int N, int tc, int32_t* __restrict__ route) {
+  const int redo = tc ? flags[0] + flags[1] : N;
+  route[0] = redo == 0 ? 1 : 2;
+  route[1] = redo;
+}
 
-int build_neighbors_tensor_core(const float* E_dev, int N, int d, int K, int32_t* out_dev, cudaStream_t s, int* fell_back);
+static size_t exact_bytes(int N, int d) { return ((size_t)N * d * sizeof(float) + 255) & ~size_t(255); }
+static bool use_tc(int N, int d, int K) {
+  return getenv("LANTERN_NBR_EXACT_ONLY") == nullptr && neighbors_tc_eligible(N, d, K);
+}
+
+extern "C" size_t lantern_build_neighbors_workspace_bytes(int32_t N, int32_t d, int32_t K) {
+  if (N < 2 || d < 1 || K < 1 || K > N - 1) return 0;
+  return exact_bytes(N, d) + (use_tc(N, d, K) ? neighbors_tc_workspace_bytes(N, d) : 0);
+}
 
 extern "C" int lantern_build_neighbors(const float* E_dev, int32_t N, int32_t d, int32_t K, int32_t* out_dev,
-                                       void* stream) {
+                                       void* workspace_dev, size_t workspace_bytes, int32_t* route_dev, void* stream) {
   using namespace lantern;
   if (!E_dev || !out_dev || N < 2 || d < 1 || K < 1 || K > N - 1) {
     set_error("lantern_build_neighbors: bad argument (need N >= 2, d >= 1, 1 <= K <= N-1)");
@@ -89,23 +109,29 @@ extern "C" int lantern_build_neighbors(const float* E_dev, int32_t N, int32_t d,
     set_error("lantern_build_neighbors: N=%d needs %zu bytes of shared memory (> 227 KB)", N, smem);
     return LANTERN_E_UNSUPPORTED;
   }
-  cudaStream_t s = static_cast<cudaStream_t>(stream);
-  if (getenv("LANTERN_NBR_EXACT_ONLY") == nullptr) {   // tensor-core path for K << N (bit-identical results)
-    int fell_back = 1;
-    const int rc = build_neighbors_tensor_core(E_dev, N, d, K, out_dev, s, &fell_back);
-    if (rc != LANTERN_OK) return rc;
-    if (!fell_back) { g_last_path = 1; return LANTERN_OK; }
+  const size_t need = lantern_build_neighbors_workspace_bytes(N, d, K);
+  if (!workspace_dev || workspace_bytes < need) {
+    set_error("lantern_build_neighbors: workspace too small (%zu < %zu)", workspace_bytes, need);
+    return LANTERN_E_WORKSPACE;
   }
-  g_last_path = 2;
-  float* Et = nullptr;
-  LANTERN_CUDA(cudaMallocAsync(&Et, (size_t)N * d * sizeof(float), s));
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  float* Et = static_cast<float*>(workspace_dev);
+  unsigned char* redo = nullptr;
+  int* flags = nullptr;
+  const bool tc = use_tc(N, d, K);
+  if (tc) {   // tensor-core candidates + exact re-rank (bit-identical results); rows it cannot finish are marked
+    const int rc = build_neighbors_tensor_core(E_dev, N, d, K, out_dev,
+                                               static_cast<unsigned char*>(workspace_dev) + exact_bytes(N, d), &redo,
+                                               &flags, s);
+    if (rc != LANTERN_OK) return rc;
+  }
+  // exact kernel: every row (no tensor-core route for this shape) or the marked rows only (the other CTAs exit at once)
   const int64_t n = (int64_t)N * d;
   transpose_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(E_dev, Et, N, d);
   if (smem > 48 * 1024)
     LANTERN_CUDA(cudaFuncSetAttribute(nbr_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  nbr_rows_kernel<<<N, kNbrThreads, smem, s>>>(E_dev, Et, N, d, K, NP, out_dev);
-  cudaError_t e = cudaGetLastError();
-  cudaFreeAsync(Et, s);
-  LANTERN_CUDA(e);
+  nbr_rows_kernel<<<N, kNbrThreads, smem, s>>>(E_dev, Et, N, d, K, NP, out_dev, redo);
+  if (route_dev) nbr_route_kernel<<<1, 1, 0, s>>>(flags, N, tc ? 1 : 0, route_dev);
+  LANTERN_CUDA(cudaGetLastError());
   return LANTERN_OK;
 }

@@ -271,8 +271,9 @@ template <int NE>
 __global__ void __launch_bounds__(kSelThreads) nbr_select_kernel(const float* __restrict__ E,
                                                                  const float* __restrict__ norms,
                                                                  const float* __restrict__ Dapprox, int ld, int N,
-                                                                 int d, int K, float max_norm,
-                                                                 int32_t* __restrict__ out, int* __restrict__ flags) {
+                                                                 int d, int K, const float* __restrict__ max_norm_dev,
+                                                                 int32_t* __restrict__ out, int* __restrict__ flags,
+                                                                 unsigned char* __restrict__ row_redo) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double* key = reinterpret_cast<double*>(smem_raw);                       // [kCandMax]
   int* cidx = reinterpret_cast<int*>(smem_raw + (size_t)kCandMax * 8);      // [kCandMax]
@@ -280,6 +281,7 @@ __global__ void __launch_bounds__(kSelThreads) nbr_select_kernel(const float* __
   __shared__ SelectSmem sm;
   __shared__ int n_cand, bad;
   const int r = blockIdx.x, tid = threadIdx.x;
+  const float max_norm = __ldg(max_norm_dev);
   const float* drow = Dapprox + (size_t)r * ld;
   float v[NE];
   // element e of thread tid is column col_of(e): 128-bit loads (rows are 16-byte aligned, ld % 4 == 0)
@@ -345,7 +347,7 @@ __global__ void __launch_bounds__(kSelThreads) nbr_select_kernel(const float* __
   __syncthreads();
   const int nc = n_cand;
   if (nc > kCandMax || nc < K) {   // overflow (massive ties) or an inconsistent GEMM: let the exact kernel handle it
-    if (tid == 0) atomicAdd(&flags[0], 1);
+    if (tid == 0) { atomicAdd(&flags[0], 1); row_redo[r] = 1; }
     return;
   }
   int np = 1;
@@ -391,7 +393,7 @@ __global__ void __launch_bounds__(kSelThreads) nbr_select_kernel(const float* __
   }
   __syncthreads();
   if (bad) {
-    if (tid == 0) atomicAdd(&flags[1], 1);
+    if (tid == 0) { atomicAdd(&flags[1], 1); row_redo[r] = 1; }
     return;
   }
   for (int size = 2; size <= np; size <<= 1) {
@@ -422,12 +424,39 @@ __global__ void max_norm_kernel(const float* __restrict__ norms, int N, float* _
 
 using namespace lantern;
 
-// norms must already hold |e_i|^2.  Packs E, then runs the persistent GEMM; D is fp32 [N, ld].
-static int launch_dist_gemm(const float* E_dev, const float* norms, int N, int d, float* D, int ld, cudaStream_t s) {
+static size_t align256(size_t x) { return (x + 255) & ~size_t(255); }
+
+// Scratch layout of the tensor-core route (all caller-owned, carved from one workspace).
+struct TcScratch {
+  size_t norms, mx, flags, redo, epk, D, total;
+  int ld, dpad, Npad;
+};
+static TcScratch tc_scratch(int N, int d) {
+  TcScratch t;
+  t.ld = (N + 7) & ~7;   // rows start on 32-byte sectors (256-bit epilogue stores)
+  t.dpad = (d + kChunkK - 1) / kChunkK * kChunkK;
+  t.Npad = (N + kTileN - 1) / kTileN * kTileN;
+  size_t o = 0;
+  t.norms = o; o += align256((size_t)N * 4);
+  t.mx = o;    o += 256;
+  t.flags = o; o += 256;
+  t.redo = o;  o += align256((size_t)N);
+  t.epk = o;   o += align256((size_t)t.Npad * t.dpad * 4);
+  t.D = o;     o += align256((size_t)N * t.ld * 4);
+  t.total = o;
+  return t;
+}
+
+bool neighbors_tc_eligible(int N, int d, int K) {
+  return !(N > kSelNE * kSelThreads || K > kCandMax / 2 || K * 2 > N || d > kGemmMaxDim);
+}
+size_t neighbors_tc_workspace_bytes(int N, int d) { return tc_scratch(N, d).total; }
+
+// norms must already hold |e_i|^2.  Packs E into Epk, then runs the persistent GEMM; D is fp32 [N, ld].
+static int launch_dist_gemm(const float* E_dev, const float* norms, int N, int d, uint32_t* Epk, float* D, int ld,
+                            cudaStream_t s) {
   const int dpad = (d + kChunkK - 1) / kChunkK * kChunkK;
   const int Npad = (N + kTileN - 1) / kTileN * kTileN;
-  uint32_t* Epk = nullptr;
-  LANTERN_CUDA(cudaMallocAsync(&Epk, (size_t)Npad * dpad * 4, s));
   pack_tf32_kernel<<<2 * kNumSMs, 256, 0, s>>>(E_dev, N, d, Npad, dpad, Epk);
   const size_t a_bytes = (size_t)dpad * kTileM * 4, stage = (size_t)kChunkK * kTileN * 4, tail = 2 * kTileN * 4;
   const size_t budget = 227 * 1024 - 512;   // static shared memory (barriers) comes out of the same 227 KiB
@@ -437,13 +466,12 @@ static int launch_dist_gemm(const float* E_dev, const float* norms, int N, int d
   const int row_blocks = (N + kTileM - 1) / kTileM, col_tiles = (N + kTileN - 1) / kTileN;
   const int gy = std::max(1, std::min(col_tiles, kNumSMs / row_blocks));
   dist_gemm_kernel<<<dim3(row_blocks, gy), kGemmThreads, smem, s>>>(Epk, norms, N, Npad, dpad, n_stages, D, ld);
-  cudaError_t e = cudaGetLastError();
-  cudaFreeAsync(Epk, s);
-  LANTERN_CUDA(e);
+  LANTERN_CUDA(cudaGetLastError());
   return LANTERN_OK;
 }
 
-// Debug / test hook: the approximate distance matrix alone (fp32 [N, ld], ld = N rounded up to 4).
+// Debug / test hook: the approximate distance matrix alone (fp32 [N, ld], ld = N rounded up to 4).  The only entry
+// that allocates (stream-ordered scratch for the packed codebook and the norms): it is not on any product path.
 extern "C" LANTERN_API int lantern_debug_dist_gemm(const float* E_dev, int32_t N, int32_t d, float* D_dev, int32_t ld,
                                                    void* stream) {
   cudaStream_t s = static_cast<cudaStream_t>(stream);
@@ -451,70 +479,46 @@ extern "C" LANTERN_API int lantern_debug_dist_gemm(const float* E_dev, int32_t N
     set_error("lantern_debug_dist_gemm: bad argument");
     return LANTERN_E_INVALID;
   }
+  const TcScratch t = tc_scratch(N, d);
   float* norms = nullptr;
+  uint32_t* Epk = nullptr;
   LANTERN_CUDA(cudaMallocAsync(&norms, (size_t)N * 4, s));
+  LANTERN_CUDA(cudaMallocAsync(&Epk, (size_t)t.Npad * t.dpad * 4, s));
   row_norms_kernel<<<(N + 255) / 256, 256, 0, s>>>(E_dev, N, d, norms);
-  int rc = launch_dist_gemm(E_dev, norms, N, d, D_dev, ld, s);
+  int rc = launch_dist_gemm(E_dev, norms, N, d, Epk, D_dev, ld, s);
   cudaFreeAsync(norms, s);
+  cudaFreeAsync(Epk, s);
   return rc;
 }
 
-// Returns LANTERN_OK and *fell_back = 0 when the tensor-core path produced the table, *fell_back = 1 when the caller
-// must run the exact kernel (unsupported shape, candidate overflow or a violated error bound).
-int build_neighbors_tensor_core(const float* E_dev, int N, int d, int K, int32_t* out_dev, cudaStream_t s,
-                                int* fell_back) {
-  *fell_back = 1;
-  if (N > kSelNE * kSelThreads || K > kCandMax / 2 || K * 2 > N || d > kGemmMaxDim) return LANTERN_OK;
-  const int ld = (N + 7) & ~7;   // rows start on 32-byte sectors (256-bit epilogue stores)
-  float *norms = nullptr, *D = nullptr, *mx = nullptr;
-  int* flags = nullptr;
-  {   // keep the (up to 1 GiB) scratch in the stream-ordered pool between calls instead of returning it to the OS
-    int dev = 0;
-    cudaMemPool_t pool;
-    if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
-      unsigned long long thr = ~0ull;
-      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
-    }
-  }
-  const bool timing = getenv("LANTERN_NBR_TIMING") != nullptr;
-  cudaEvent_t ev[3];
-  if (timing) for (auto& e : ev) cudaEventCreate(&e);
-  LANTERN_CUDA(cudaMallocAsync(&norms, (size_t)N * 4, s));
-  LANTERN_CUDA(cudaMallocAsync(&mx, 4, s));
-  LANTERN_CUDA(cudaMallocAsync(&flags, 8, s));
-  LANTERN_CUDA(cudaMallocAsync(&D, (size_t)N * ld * 4, s));
-  LANTERN_CUDA(cudaMemsetAsync(flags, 0, 8, s));
-  if (timing) cudaEventRecord(ev[0], s);
+// Tensor-core route: candidates from the tcgen05 distance GEMM, exact fp64 re-rank per row.  Rows the route cannot
+// finish (candidate overflow, violated error bound) are marked in row_redo for the exact kernel; nothing here
+// synchronises or allocates.  flags_dev[0..1] count those rows.
+int build_neighbors_tensor_core(const float* E_dev, int N, int d, int K, int32_t* out_dev, void* workspace,
+                                unsigned char** row_redo_out, int** flags_out, cudaStream_t s) {
+  const TcScratch t = tc_scratch(N, d);
+  unsigned char* w = static_cast<unsigned char*>(workspace);
+  float* norms = reinterpret_cast<float*>(w + t.norms);
+  float* mx = reinterpret_cast<float*>(w + t.mx);
+  int* flags = reinterpret_cast<int*>(w + t.flags);
+  unsigned char* redo = w + t.redo;
+  uint32_t* Epk = reinterpret_cast<uint32_t*>(w + t.epk);
+  float* D = reinterpret_cast<float*>(w + t.D);
+  LANTERN_CUDA(cudaMemsetAsync(w + t.flags, 0, 256 + align256((size_t)N), s));   // flags + row_redo (adjacent)
   row_norms_kernel<<<(N + 255) / 256, 256, 0, s>>>(E_dev, N, d, norms);
   max_norm_kernel<<<1, 512, 0, s>>>(norms, N, mx);
-  { int rc = launch_dist_gemm(E_dev, norms, N, d, D, ld, s); if (rc != LANTERN_OK) return rc; }
-  if (timing) cudaEventRecord(ev[1], s);
-  float h_mx = 0.f;
-  LANTERN_CUDA(cudaMemcpyAsync(&h_mx, mx, 4, cudaMemcpyDeviceToHost, s));
-  LANTERN_CUDA(cudaStreamSynchronize(s));
+  { int rc = launch_dist_gemm(E_dev, norms, N, d, Epk, D, t.ld, s); if (rc != LANTERN_OK) return rc; }
   const size_t sel_smem = (size_t)kCandMax * 12 + (size_t)kGemmMaxDim * 8;
   auto run_select = [&](auto kern) -> cudaError_t {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sel_smem);
     if (e != cudaSuccess) return e;
-    kern<<<N, kSelThreads, sel_smem, s>>>(E_dev, norms, D, ld, N, d, K, h_mx, out_dev, flags);
+    kern<<<N, kSelThreads, sel_smem, s>>>(E_dev, norms, D, t.ld, N, d, K, mx, out_dev, flags, redo);
     return cudaGetLastError();
   };
   if (N <= 8 * kSelThreads) LANTERN_CUDA(run_select(nbr_select_kernel<8>));
   else if (N <= 16 * kSelThreads) LANTERN_CUDA(run_select(nbr_select_kernel<16>));
   else LANTERN_CUDA(run_select(nbr_select_kernel<kSelNE>));
-  if (timing) cudaEventRecord(ev[2], s);
-  int h_flags[2] = {0, 0};
-  LANTERN_CUDA(cudaMemcpyAsync(h_flags, flags, 8, cudaMemcpyDeviceToHost, s));
-  LANTERN_CUDA(cudaStreamSynchronize(s));
-  if (timing) {
-    float g = 0.f, q = 0.f;
-    cudaEventElapsedTime(&g, ev[0], ev[1]);
-    cudaEventElapsedTime(&q, ev[1], ev[2]);
-    fprintf(stderr, "[lantern] neighbours N=%d d=%d K=%d: distance GEMM %.3f ms, select+rerank %.3f ms, flags overflow=%d bound=%d\n", N, d, K, g, q, h_flags[0], h_flags[1]);
-    for (auto& e : ev) cudaEventDestroy(e);
-  }
-  cudaFreeAsync(norms, s); cudaFreeAsync(mx, s); cudaFreeAsync(flags, s); cudaFreeAsync(D, s);
-  LANTERN_CUDA(cudaGetLastError());
-  *fell_back = (h_flags[0] || h_flags[1]) ? 1 : 0;
+  *row_redo_out = redo;
+  *flags_out = flags;
   return LANTERN_OK;
 }

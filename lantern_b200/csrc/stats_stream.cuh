@@ -59,7 +59,7 @@ struct StreamSmem {
 
 // mbarrier wait that backs off between polls: a spinning warp would otherwise take issue slots from the warps it
 // is waiting for (they share the SM's schedulers)
-__device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity, bool sleep = true) {
+__device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity, unsigned sleep_ns = 40) {
   uint32_t done;
   asm volatile(
       "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
@@ -67,7 +67,7 @@ __device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity
       : "r"(smem_u32(bar)), "r"(parity)
       : "memory");
   while (!done) {
-    if (sleep) __nanosleep(40);
+    if (sleep_ns) __nanosleep(sleep_ns);
     asm volatile(
         "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
         : "=r"(done)
@@ -153,8 +153,7 @@ __global__ void __launch_bounds__(NT + 64, (NT <= 256 ? 2 : 1)) row_stats_stream
       if (kind != LANTERN_ROW_IMAGE) continue;     // one-hot rows never reach the select warps
       if ((jj & 1) != my_parity) { ++jj; continue; }
       const int hb = (int)(jj & 1);                       // hand-over buffer of this row
-      mbar_wait_backoff(&fs.mbar_ready[hb], (jj >> 1) & 1, !(P.dbg & 2));
-      const long long t_sel0 = (P.dbg & 4) ? clock64() : 0;
+      mbar_wait_backoff(&fs.mbar_ready[hb], (jj >> 1) & 1, 200);   // two row periods of slack: poll rarely
       const float* my_seg = seg + (hb * NW + w_seg) * kSegCap;
       unsigned* hist = fs.hist[hb];
       const RowDesc& dsc = fs.desc[hb];
@@ -167,19 +166,6 @@ __global__ void __launch_bounds__(NT + 64, (NT <= 256 ? 2 : 1)) row_stats_stream
       const int n_w = (int)(__shfl_sync(0xffffffffu, cw, w_seg) >> 16);
       const int k = cfg.top_k;
       bool ok = !(flags & kRowRedo) && !overflow;
-      if (P.dbg & 1) {   // experiment: no select work at all
-        if (sl == 0) {
-          RowStats st;
-          st.thr = 0.f; st.mx = m; st.sum = 1.f; st.vcut = -INFINITY; st.icut = -1; st.kind = 0; st.pad0 = st.pad1 = 0;
-          P.stats[row] = st;
-        }
-        hist[2 * sl] = 0u;
-        hist[2 * sl + 1] = 0u;
-        __syncwarp();
-        if (sl == 0) mbar_arrive(&fs.mbar_done[hb]);
-        ++jj;
-        continue;
-      }
       float thr = -INFINITY;
       bool hit = false;
       float part = sl < NW ? fs.sab_part[hb][sl] : 0.f;   // kept mass above the bracket, summed by the main warps
@@ -188,7 +174,7 @@ __global__ void __launch_bounds__(NT + 64, (NT <= 256 ? 2 : 1)) row_stats_stream
         ok = tot_above < k && k <= tot_above + tot_in;
         if (ok) {
           const int krem = k - tot_above;      // rank among the parked elements (1-based from the top)
-          const int trips = __reduce_max_sync(0xffffffffu, (n_w + LPS - 1) / LPS);
+          const int trips = __reduce_max_sync(0xffffffffu, (n_w + 4 * LPS - 1) / (4 * LPS));
           float lo = lo0, hi = hi0;
           ok = false;
 #pragma unroll 1
@@ -227,17 +213,23 @@ __global__ void __launch_bounds__(NT + 64, (NT <= 256 ? 2 : 1)) row_stats_stream
               // (ballot prefix, not atomics): the sum stays reproducible bit for bit
               int n_cand = 0;
               float acc = 0.f;
-#pragma unroll 2
-              for (int t = 0; t < trips; ++t) {
-                const int i = sub + t * LPS;
-                const bool valid = i < n_w;
-                const float v = valid ? my_seg[i] : 0.f;
-                const unsigned f = cls(v);
-                if (valid && f > F) acc += ex(v);
-                const bool is_f = valid && f == F;
-                const unsigned mk = __ballot_sync(0xffffffffu, is_f);
-                if (is_f) cand[n_cand + __popc(mk & ((1u << sl) - 1u))] = v;
-                n_cand += __popc(mk);
+#pragma unroll 1
+              for (int t = 0; t < trips; ++t) {      // four consecutive elements per lane and trip (one 128-bit read)
+                const int i = (t * LPS + sub) * 4;
+                const float4 q = *reinterpret_cast<const float4*>(my_seg + i);
+                const float v4[4] = {q.x, q.y, q.z, q.w};
+                unsigned f4[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) f4[j] = cls(v4[j]);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  const bool valid = i + j < n_w;
+                  if (valid && f4[j] > F) acc += ex(v4[j]);
+                  const bool is_f = valid && f4[j] == F;
+                  const unsigned mk = __ballot_sync(0xffffffffu, is_f);
+                  if (is_f) cand[n_cand + __popc(mk & ((1u << sl) - 1u))] = v4[j];
+                  n_cand += __popc(mk);
+                }
               }
               __syncwarp();
               const int kr = krem - above2;
@@ -316,9 +308,6 @@ __global__ void __launch_bounds__(NT + 64, (NT <= 256 ? 2 : 1)) row_stats_stream
         else win_run = fminf(0.25f, 2.0f * fmaxf(win_run, P.win_sd));
       }
       if (sl == 0) fs.zbuf[hb] = make_float2(z_run, win_run);
-      if ((P.dbg & 4) && sl == 0 && blockIdx.x == 0)
-        printf("select row %u: parked %d above %d hit %d cycles %lld win %.3f\n", jj, tot_in, tot_above, (int)hit,
-               clock64() - t_sel0, win_run);
       __syncwarp();
       if (sl == 0) mbar_arrive(&fs.mbar_done[hb]);
       ++jj;
@@ -341,23 +330,32 @@ __global__ void __launch_bounds__(NT + 64, (NT <= 256 ? 2 : 1)) row_stats_stream
 
     // ---- pass 1: lift the staged row into registers: CFG mix (+ temperature) + per-thread statistics ----
     mbar_wait(&fs.mbar_tma, parity);
+
     parity ^= 1;
     float s[NE];
-    float fsum = 0.f, fsq = 0.f, fmx = -INFINITY;
+    float fsum, fsq, fmx = -INFINITY;
+    {
+      uint64_t sum2 = pack2(0.f, 0.f), sq2 = pack2(0.f, 0.f);   // even / odd elements: the moments only steer the bracket
 #pragma unroll
-    for (int q = 0; q < NQ; ++q) {
-      const int e0 = (q * NT + tid) * 4;
-      float c4[4], u4[4] = {0.f, 0.f, 0.f, 0.f};
-      lds4<DT>(buf_c + lead_c, e0, c4);
-      if (MODE == 1) lds4<DT>(buf_u + lead_u, e0, u4);
+      for (int q = 0; q < NQ; ++q) {
+        const int e0 = (q * NT + tid) * 4;
+        float c4[4], u4[4] = {0.f, 0.f, 0.f, 0.f};
+        lds4<DT>(buf_c + lead_c, e0, c4);
+        if (MODE == 1) lds4<DT>(buf_u + lead_u, e0, u4);
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float v = mix_temper(c4[j], u4[j], mix);
-        s[q * 4 + j] = v;
-        fsum += v;
-        fsq = fmaf(v, v, fsq);
-        fmx = fmaxf(fmx, v);
+        for (int j = 0; j < 4; j += 2) {
+          const uint64_t v2 = mix_temper2(c4[j], c4[j + 1], u4[j], u4[j + 1], mix);
+          unpack2(v2, s[q * 4 + j], s[q * 4 + j + 1]);
+          sum2 = add2(sum2, v2);
+          sq2 = fma2(v2, v2, sq2);
+          fmx = fmaxf(fmx, fmaxf(s[q * 4 + j], s[q * 4 + j + 1]));
+        }
       }
+      float a, b;
+      unpack2(sum2, a, b);
+      fsum = a + b;
+      unpack2(sq2, a, b);
+      fsq = a + b;
     }
     fsum = warp_reduce(fsum, OpSum());
     fsq = warp_reduce(fsq, OpSum());
@@ -397,9 +395,8 @@ __global__ void __launch_bounds__(NT + 64, (NT <= 256 ? 2 : 1)) row_stats_stream
     // the hand-over buffers of this row were last used two rows ago: the select warp has normally long finished that
     // row; what it observed there steers this row's bracket
     const int hb = (int)(jj & 1);
-    const long long t_w0 = (P.dbg & 4) ? clock64() : 0;
-    mbar_wait_backoff(&fs.mbar_done[hb], ((jj >> 1) & 1) ^ 1, !(P.dbg & 2));
-    if ((P.dbg & 4) && tid == 0 && blockIdx.x == 0) printf("main row %u: waited %lld cycles for select, t=%lld\n", jj, clock64() - t_w0, clock64());
+    mbar_wait_backoff(&fs.mbar_done[hb], ((jj >> 1) & 1) ^ 1, 40);
+
     ++jj;
     float lo, hi;
     bool good = isfinite(fmx) && isfinite(fsq);     // -inf / +inf / NaN elements: the redo path handles the row
@@ -494,7 +491,6 @@ __global__ void __launch_bounds__(NT + 64, (NT <= 256 ? 2 : 1)) row_stats_stream
     if (lane == 0) mbar_arrive(&fs.mbar_ready[hb]);
   }
   __syncthreads();   // pairs with the select warp's final barrier
-  if ((P.dbg & 4) && tid == 0 && blockIdx.x < 4) printf("cta %d redo_n %d of %u rows\n", (int)blockIdx.x, fs.redo_n, it_row);
   if (fs.redo_n == 0) return;
 
   // ---- redo: rows the streaming select could not finish; exact tiers 2 / 3 on the re-staged row ----

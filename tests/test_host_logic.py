@@ -21,7 +21,7 @@ def test_library_exports_every_declared_symbol():
     lib = _abi.load()
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.lantern_version() >> 16 == 1
+    assert lib.lantern_version() >> 16 == 2     # LANTERN_ABI_VERSION (2: caller-owned scratch for lantern_build_neighbors)
     assert lib.lantern_last_error() is not None
 
 

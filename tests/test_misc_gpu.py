@@ -201,13 +201,16 @@ def test_tensor_core_neighbor_table_bit_exact(N, d, K):
     E /= np.linalg.norm(E, axis=1, keepdims=True)
     E[5] = E[N // 3]                                   # duplicate row: tie broken by id
     want = O.neighbor_table(E, K)
-    got = codebook.build_neighbor_table(torch.from_numpy(E).cuda(), k=K).cpu().numpy()
-    assert _abi.load().lantern_debug_neighbors_path() == 1, "tensor-core path fell back to the fp64 kernel"
+    got, route = codebook.build_neighbor_table(torch.from_numpy(E).cuda(), k=K, return_route=True)
+    got = got.cpu().numpy()
+    assert route.tolist() == [1, 0], "tensor-core route sent rows to the fp64 kernel"
     assert np.array_equal(got, want)
     os_env = __import__("os").environ
     os_env["LANTERN_NBR_EXACT_ONLY"] = "1"             # the all-fp64 route gives the same table
     try:
-        exact = codebook.build_neighbor_table(torch.from_numpy(E).cuda(), k=K).cpu().numpy()
+        exact, route = codebook.build_neighbor_table(torch.from_numpy(E).cuda(), k=K, return_route=True)
+        exact = exact.cpu().numpy()
+        assert route.tolist() == [2, N]
     finally:
         del os_env["LANTERN_NBR_EXACT_ONLY"]
     assert np.array_equal(exact, want)

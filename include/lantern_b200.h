@@ -137,7 +137,9 @@ typedef struct lantern_accept_out {
 LANTERN_API int lantern_version(void);
 LANTERN_API const char* lantern_last_error(void);
 
-/* Scratch the fused step needs for `cfg` (per-row softmax statistics). */
+/* Scratch the fused step needs for `cfg`: 32 bytes of softmax statistics per logits row, plus one fp32 probability
+ * vector per prompt when the live window is too wide for shared memory (more than ~50K columns, e.g. plain EAGLE
+ * verification on a 65536-entry vocabulary; such rows take a multi-pass statistics kernel - a parity path, not tuned). */
 LANTERN_API size_t lantern_accept_workspace_bytes(const lantern_accept_cfg* cfg);
 
 /*

@@ -25,6 +25,7 @@
 #include "select.cuh"
 #include "stats_fast.cuh"
 #include "stats_stream.cuh"
+#include "stats_wide.cuh"
 #include "topp.cuh"
 
 namespace lantern {
@@ -362,7 +363,11 @@ __global__ void __launch_bounds__(LNE > 0 ? kLazyThreads : kWalkThreads) walk_ke
   // ---- carve shared memory ----
   WalkSmem S;
   size_t o = 0;
-  S.p = reinterpret_cast<float*>(smem_raw + o);            o += (size_t)((ncols + 3) & ~3) * 4;
+  if (P.p_spill) {   // very wide windows: the probability vector lives in global memory (L2), one slice per prompt
+    S.p = P.p_spill + (size_t)b * (size_t)((ncols + 3) & ~3);
+  } else {
+    S.p = reinterpret_cast<float*>(smem_raw + o);          o += (size_t)((ncols + 3) & ~3) * 4;
+  }
   S.nbmask = reinterpret_cast<unsigned*>(smem_raw + o);     o += (size_t)(((ncols + 31) >> 5) + 3 & ~3) * 4;
   S.dscr = reinterpret_cast<double*>(smem_raw + o);         o += 34 * 8;
   S.ri = reinterpret_cast<int*>(smem_raw + o);              o += (size_t)((L * D + 3) & ~3) * 4;
@@ -801,9 +806,9 @@ __global__ void __launch_bounds__(LNE > 0 ? kLazyThreads : kWalkThreads) walk_ke
 // ----------------------------------------------------------------------------------------------
 // Host side
 // ----------------------------------------------------------------------------------------------
-static size_t walk_smem_bytes(const lantern_accept_cfg& c, int lazy_ne) {
+static size_t walk_smem_bytes(const lantern_accept_cfg& c, int lazy_ne, bool spill = false) {
   size_t o = (size_t)lazy_ne * kLazyThreads * 4;
-  o += (size_t)((c.ncols + 3) & ~3) * 4;
+  if (!spill) o += (size_t)((c.ncols + 3) & ~3) * 4;
   o += (size_t)((((c.ncols + 31) >> 5) + 3) & ~3) * 4;
   o += 34 * 8;
   o += (size_t)((c.n_paths * c.depth + 3) & ~3) * 4;
@@ -863,7 +868,8 @@ static int launch_all(const AcceptParams& P_in, cudaStream_t stream, int phases)
   const size_t park_bytes = (use_stream ? (size_t)ps_slots * nt * sizeof(float) + 2 * (size_t)(nt / 32) * kSegCap * sizeof(float)
                                     : (size_t)nq_inst * 4 * nt * sizeof(float)) +
                             (mode == 1 ? 2 : (mode == 2 ? 1 : 0)) * stage_bytes;
-  if (park_bytes + 6 * 1024 > 227 * 1024) {
+  const bool wide = !full && c.ncols > 16 * 4 * 512;   // multi-pass kernel, no register-resident row
+  if (!wide && park_bytes + 6 * 1024 > 227 * 1024) {
     set_error("row statistics kernel needs %zu bytes of shared memory", park_bytes);
     return LANTERN_E_UNSUPPORTED;
   }
@@ -908,6 +914,8 @@ static int launch_all(const AcceptParams& P_in, cudaStream_t stream, int phases)
     else LAUNCH_FAST_MODE(NT, NQ, 2);           \
   } while (0)
   if (!(phases & 1) || (phases & 4)) {
+  } else if (wide) {   // wider than the register-resident limit: multi-pass kernel
+    row_stats_wide_kernel<DT><<<(unsigned)std::min<long long>(rows, 4LL * kNumSMs), kWideThreads, 0, stream>>>(P);
   } else if (mode) {
     if (nt == 256 && nq_inst == 2) LAUNCH_FAST(256, 2);
     else if (nt == 256 && nq_inst == 4) LAUNCH_FAST(256, 4);
@@ -953,7 +961,7 @@ static int launch_all(const AcceptParams& P_in, cudaStream_t stream, int phases)
     set_error("lazy statistics need a vector-aligned window of 2048/4096/8192/16384 columns and no top-p");
     return LANTERN_E_UNSUPPORTED;
   }
-  const size_t smem = walk_smem_bytes(c, lazy_ne);
+  const size_t smem = walk_smem_bytes(c, lazy_ne, P.p_spill != nullptr);
   if (smem > 227 * 1024) {
     set_error("walk kernel needs %zu bytes of shared memory (> 227 KB): ncols too large", smem);
     return LANTERN_E_UNSUPPORTED;
@@ -981,9 +989,17 @@ static int launch_all(const AcceptParams& P_in, cudaStream_t stream, int phases)
 
 using namespace lantern;
 
+// the walk's probability vector spills to global memory when the shared-memory carve-up would not fit
+static bool walk_spills(const lantern_accept_cfg& c) { return walk_smem_bytes(c, 0, false) > 227 * 1024; }
+static size_t stats_bytes(const lantern_accept_cfg& c) {
+  return ((size_t)c.n_items * (size_t)c.n_rows * sizeof(RowStats) + 255) & ~size_t(255);
+}
+
 extern "C" size_t lantern_accept_workspace_bytes(const lantern_accept_cfg* cfg) {
   if (!cfg) return 0;
-  return (size_t)cfg->n_items * (size_t)cfg->n_rows * sizeof(RowStats);
+  size_t n = stats_bytes(*cfg);
+  if (walk_spills(*cfg)) n += (size_t)cfg->n_items * (size_t)((cfg->ncols + 3) & ~3) * sizeof(float);
+  return n;
 }
 
 // Acklam's rational approximation of the inverse normal CDF (|error| < 1.2e-9); only seeds a search bracket.
@@ -1044,6 +1060,8 @@ static void fill_params(AcceptParams& P, const lantern_accept_cfg* cfg, const la
   P.in = *in;
   if (out) P.out = *out; else memset(&P.out, 0, sizeof(P.out));
   P.stats = static_cast<RowStats*>(workspace_dev);
+  P.p_spill = (workspace_dev && walk_spills(*cfg))
+                  ? reinterpret_cast<float*>(static_cast<unsigned char*>(workspace_dev) + stats_bytes(*cfg)) : nullptr;
   P.mix.cfg_scale = cfg->cfg_scale;
   P.mix.temperature = cfg->temperature;
   P.mix.has_uncond = in->logits_uncond != nullptr;

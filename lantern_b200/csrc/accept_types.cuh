@@ -21,6 +21,8 @@ struct AcceptParams {
   lantern_accept_in in;
   lantern_accept_out out;
   RowStats* stats;
+  float* p_spill;  // [n_items, ncols rounded up to 4] walk probability vectors in global memory when they do not fit
+                   // in shared memory (more than ~50K live columns); NULL otherwise
   MixParams mix;
   int vec_ok;     // rows can be read with 4-element vector loads
   int do_topk;    // 0 < top_k < ncols

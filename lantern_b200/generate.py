@@ -163,47 +163,56 @@ class StandInEngine:
         return out
 
     def _run_chunk(self, idx: List[int], stride: int) -> List[Dict]:
+        """Lockstep loop of one chunk.  Per step the host issues the fused verify launch and one tiny copy; everything
+        else (which row serves which prompt, the uniforms of a block of steps) is prepared per block of ``sync_every``
+        steps, and the per-prompt bookkeeping is done afterwards from the [steps, B] matrix of accepted lengths -
+        prompts that are already complete keep stepping and are ignored."""
         torch = self.torch
         B, P, T = len(idx), self.P, self.T
         dev = self.dev
         need = self.tokens_per_image
         pid = torch.tensor(idx, device=dev, dtype=torch.long)
-        produced = torch.zeros(B, device=dev, dtype=torch.int32)
-        steps_used = torch.zeros(B, device=dev, dtype=torch.int32)
-        hist = torch.zeros(B, self.D + 1, device=dev, dtype=torch.int32)
-        finish_step = [-1] * B
-        finish_time = [0.0] * B
+        ar = torch.arange(B, device=dev)
+        every = self.args.sync_every
+        tok_cache, ret_cache = {}, {}
+        blocks, times = [], []
+        produced = torch.zeros(B, device=dev, dtype=torch.int64)
         torch.cuda.synchronize(dev)
         t0 = time.perf_counter()
         s = 0
-        ar = torch.arange(B, device=dev)
         while True:
-            for _ in range(self.args.sync_every):
+            acc = torch.empty(every, B, device=dev, dtype=torch.int32)
+            srange = torch.arange(s, s + every, device=dev)
+            uni_blk = self.uni_pool[(pid[None, :] * 31 + srange[:, None] * 17) % self.uni_pool.shape[0]]   # [every, B, T+1]
+            for j in range(every):
                 start = (idx[0] + s) % P                         # row of prompt i at step s: (i + s) mod P
-                rows = start + stride * ar                       # < 2P: the pool is stored twice
-                view = lambda t: t[start:start + stride * (B - 1) + 1:stride]
-                uni = self.uni_pool[(pid * 31 + s * 17) % self.uni_pool.shape[0]]
-                res = self.ver.step(view(self.cond), view(self.uncond), self.tokens[rows], self.retrieve[rows],
-                                    uniforms=uni)
-                live = produced < need
-                a1 = res.accept_length + 1
-                produced += torch.where(live, a1, torch.zeros_like(a1))
-                steps_used += live.to(torch.int32)
-                hist[ar, res.accept_length.long()] += live.to(torch.int32)
+                if start not in tok_cache:                       # at most P distinct windows: gathered once each
+                    rows = start + stride * ar                   # < 2P: the pool is stored twice
+                    tok_cache[start], ret_cache[start] = self.tokens[rows], self.retrieve[rows]
+                hi = start + stride * (B - 1) + 1
+                res = self.ver.step(self.cond[start:hi:stride], self.uncond[start:hi:stride], tok_cache[start],
+                                    ret_cache[start], uniforms=uni_blk[j])
+                acc[j] = res.accept_length
                 s += 1
-            done = (produced >= need).cpu().tolist()             # one host sync per `sync_every` steps
-            now = time.perf_counter() - t0
-            for b in range(B):
-                if done[b] and finish_step[b] < 0:
-                    finish_step[b], finish_time[b] = s, now
-            if all(done):
+            produced += (acc.long() + 1).sum(0)
+            blocks.append(acc)
+            done = bool((produced >= need).all())                # one host sync per `sync_every` steps
+            times.append(time.perf_counter() - t0)
+            if done:
                 break
-        torch.cuda.synchronize(dev)
         wall = time.perf_counter() - t0
-        prod, used, hh = produced.cpu().tolist(), steps_used.cpu().tolist(), hist.cpu().tolist()
-        return [{"index": idx[b], "tokens": int(prod[b]), "steps": int(used[b]),
-                 "step_compression": prod[b] / max(1, used[b]), "latency": finish_time[b],
-                 "accept_histogram": hh[b], "rank_wall_s": wall, "batch": B} for b in range(B)]
+        a = torch.cat(blocks).cpu().numpy().astype("int64")      # [steps, B]
+        import numpy as np
+        cum = np.cumsum(a + 1, axis=0)
+        out = []
+        for b in range(B):
+            n_steps = int(np.argmax(cum[:, b] >= need)) + 1      # steps until the prompt had all its tokens
+            hist = np.bincount(a[:n_steps, b], minlength=self.D + 1)
+            out.append({"index": idx[b], "tokens": int(cum[n_steps - 1, b]), "steps": n_steps,
+                        "step_compression": float(cum[n_steps - 1, b]) / n_steps,
+                        "latency": times[(n_steps - 1) // every], "accept_histogram": hist.tolist(),
+                        "rank_wall_s": wall, "batch": B})
+        return out
 
 
 def run_generate_image(args, engine_factory: Optional[Callable] = None) -> Dict:

@@ -351,9 +351,12 @@ __device__ __forceinline__ bool lazy_probs(const AcceptParams& P, int b, int nod
   return false;
 }
 
+// LNE > 0: lazy form (512 threads, the walk computes the statistics of the rows it visits); LNE == 0: the walk behind
+// the streamed row-statistics kernel (1024 threads).
 template <int DT, bool VEC, int LNE>
 __global__ void __launch_bounds__(LNE > 0 ? kLazyThreads : kWalkThreads) walk_kernel(const AcceptParams P) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
+  using WB = BlockBar;   // the threads that walk: the whole CTA
   const lantern_accept_cfg& cfg = P.cfg;
   const int b = blockIdx.x, tid = threadIdx.x, NT = blockDim.x;
   const int L = cfg.n_paths, D = cfg.depth, T = cfg.n_rows, V = cfg.vocab;
@@ -381,7 +384,9 @@ __global__ void __launch_bounds__(LNE > 0 ? kLazyThreads : kWalkThreads) walk_ke
   S.fscr = reinterpret_cast<float*>(smem_raw + o);          o += 36 * 4;
   S.iscr = reinterpret_cast<int*>(smem_raw + o);            o += 40 * 4;
   S.pid = reinterpret_cast<int*>(smem_raw + o);                 o += (size_t)((L + 3) & ~3) * 4;
-  float* lazy_park = reinterpret_cast<float*>(smem_raw + o);   // [LNE][kLazyThreads] (lazy mode only)
+  o = (o + 7) & ~size_t(7);
+  double* rsum = reinterpret_cast<double*>(smem_raw + o);       o += 2 * 32 * 8;   // removed-mass partials, two parities
+  float* lazy_park = reinterpret_cast<float*>(smem_raw + o);   // [LNE][kLazyThreads] (lazy modes only)
   __shared__ SelectSmem lazy_sm;
   __shared__ float lazy_part[32];
   float z_run = P.z_guess, win_run = P.win_sd_first;
@@ -397,7 +402,7 @@ __global__ void __launch_bounds__(LNE > 0 ? kLazyThreads : kWalkThreads) walk_ke
     else uv = philox_uniform(cfg.philox_seed, cfg.philox_step, (uint32_t)b, (uint32_t)i);
     S.uni[i] = uv;
   }
-  __syncthreads();
+  WB::sync();
   auto cand = [&](int j, int i) -> int {
     const int n = S.ri[j * D + i];
     return n >= 0 ? S.tok[n] : -1;
@@ -409,7 +414,7 @@ __global__ void __launch_bounds__(LNE > 0 ? kLazyThreads : kWalkThreads) walk_ke
     const int root_tok = cand(0, 0);
     for (int j = tid; j < L; j += NT) member[j] = cand(j, 0) == root_tok ? 1 : 0;
   }
-  __syncthreads();
+  WB::sync();
 
   // ---- distribution state: window S.p + one explicit out-of-window token + uniform remainder ----
   // The residual is stored unnormalised: probability = stored value * scale.  A rejection then only zeroes
@@ -431,6 +436,14 @@ __global__ void __launch_bounds__(LNE > 0 ? kLazyThreads : kWalkThreads) walk_ke
     m.do_temp = 0;
     return mix_temper(c, u, m);
   };
+  // which node's distribution S.p holds, and whether a rejection has modified it since (the fresh tail can reuse it)
+  int dist_node = -1;
+  bool dist_dirty = false, dist_raw = false;
+  // fp64 sum of the window S.p, kept up to date across zeroing rejections (a rejection then only reduces the mass it
+  // removed instead of re-summing the whole vector); invalid after a fresh distribution or a static-tree subtraction
+  double win_tot = 0.0;
+  bool win_tot_valid = false;
+  unsigned rej_parity = 0;
   auto set_distribution = [&](int node, bool raw) {
     const long long row = (long long)b * T + node;
     RowStats st;
@@ -439,15 +452,18 @@ __global__ void __launch_bounds__(LNE > 0 ? kLazyThreads : kWalkThreads) walk_ke
     } else {
       st = P.stats[row];
     }
-    __syncthreads();
+    WB::sync();
     extra_tok = -1; p_extra = 0.f; p_out = 0.f; scale = 1.0f;
+    dist_node = node; dist_dirty = false; dist_raw = raw;
+    win_tot_valid = false;
     int kind = st.kind;
     if (kind == LANTERN_ROW_IMAGE) {
-      ++rows_read;
       bool empty;
       if (LNE > 0) {
+        ++rows_read;
         empty = lazy_probs<DT, (LNE > 0 ? LNE : 4)>(P, b, node, raw, S.p, lazy_park, lazy_sm, lazy_part, z_run, win_run);
       } else {
+        ++rows_read;
         if (raw) st = raw_row_stats<DT, VEC>(P, b, node, S.fscr, S.dscr);
         empty = st.mx == -INFINITY;
         if (!empty) load_probs<DT, VEC>(P, b, node, st, S.p, raw);
@@ -468,13 +484,13 @@ __global__ void __launch_bounds__(LNE > 0 ? kLazyThreads : kWalkThreads) walk_ke
         extra_tok = kind == LANTERN_ROW_NEWLINE ? cfg.newline_token : cfg.eoi_token;
         p_extra = 1.0f;
         if (extra_tok >= col0 && extra_tok < col1) {   // degenerate configs: keep it inside the window
-          __syncthreads();
+          WB::sync();
           if (tid == 0) S.p[extra_tok - col0] = 1.0f;
           extra_tok = -1; p_extra = 0.f;
         }
       }
     }
-    __syncthreads();
+    WB::sync();
   };
   auto uniform = [&](int d) -> float { return S.uni[min(d, T)]; };
   auto is_syntax = [&](int tkn) -> bool {
@@ -519,7 +535,7 @@ __global__ void __launch_bounds__(LNE > 0 ? kLazyThreads : kWalkThreads) walk_ke
       }
       if (tid == 0) { S.iscr[38] = n; S.iscr[35] = first_member < 0 ? 0 : first_member; }
     }
-    __syncthreads();
+    WB::sync();
     const int n_kids = S.iscr[38], fi = S.iscr[35];   // fi: first row still matching the accepted prefix
     if (cfg.lantern && tid < n_kids) {   // pull the children's neighbour-table rows towards L2 behind the row load
       const int xk = S.tried[tid] - off;
@@ -599,7 +615,7 @@ __global__ void __launch_bounds__(LNE > 0 ? kLazyThreads : kWalkThreads) walk_ke
           if (t0 < kk) v0 = (double)prob_of(__ldg(nb_row + t0) + off);
           if (ept == 2 && t0 + 1 < kk) v1 = (double)prob_of(__ldg(nb_row + t0 + 1) + off);
           double total;
-          const double incl1 = carry + block_scan_incl(v0 + v1, S.dscr, &total);   // prefix through the thread's last neighbour
+          const double incl1 = carry + block_scan_incl<WB>(v0 + v1, S.dscr, &total);   // prefix through the thread's last neighbour
           const float cs0 = (float)((incl1 - v1) * (double)scale);
           const float cs1 = (float)(incl1 * (double)scale);
           int fail = 0x7fffffff;                         // sums are non-decreasing: the failures form a suffix
@@ -609,12 +625,12 @@ __global__ void __launch_bounds__(LNE > 0 ? kLazyThreads : kWalkThreads) walk_ke
           if (ept == 2) S.csv[tid * ept + 1] = cs1;
           const int wfail = __reduce_min_sync(0xffffffffu, fail);
           if ((tid & 31) == 0 && wfail != 0x7fffffff) atomicMin(&S.iscr[39], wfail);
-          __syncthreads();
+          WB::sync();
           const int cnt = S.iscr[39];
           if (cnt > 0) S.fscr[35] = S.csv[cnt - 1];      // every thread stores the same value
           n_ok += cnt;
           carry += total;
-          __syncthreads();
+          WB::sync();
           if (cnt < chunk) break;
         }
         if (n_ok > 0) {
@@ -629,21 +645,23 @@ __global__ void __launch_bounds__(LNE > 0 ? kLazyThreads : kWalkThreads) walk_ke
         accepted = true;
         for (int jj = tid; jj < L; jj += NT)     // rows that continue with token x
           if (member[jj] && cand(jj, lvl) != x) member[jj] = 0;
-        __syncthreads();
+        WB::sync();
         break;
       }
       // ---------------- rejection: residual distribution ----------------
+      dist_dirty = true;
       // every thread must have read this candidate's probabilities (px, first prefix sum) before any entry is zeroed:
       // the shortcuts above can reach this point without passing a barrier
-      __syncthreads();
+      WB::sync();
       const bool zero_nb = cfg.lantern && relaxable && idx != -1;
+      double removed = 0.0;
       if (cfg.static_tree) {
         const float* q = P.in.draft_op + ((size_t)b * cfg.n_q_rows + P.in.node_qrow[cnode]) * (size_t)V;
         const int s0 = P.in.sib_off[cnode], s1 = min(P.in.sib_off[cnode + 1], s0 + kMaxSib);
         const int* sib_tok = P.in.sib_tokens + (size_t)b * P.in.sib_tokens_stride;
-        __syncthreads();
+        WB::sync();
         for (int s = s0 + tid; s < s1; s += NT) S.sib[s - s0] = sib_tok[P.in.sib_idx[s]];
-        __syncthreads();
+        WB::sync();
         const int nsib = s1 - s0;
         auto is_sib = [&](int tkn) -> bool {
           bool hit = false;
@@ -654,12 +672,12 @@ __global__ void __launch_bounds__(LNE > 0 ? kLazyThreads : kWalkThreads) walk_ke
         if (s1 > s0) {   // q[earlier siblings] = 0; q /= q.sum()
           double part = 0.0;
           for (int v = tid; v < V; v += NT) part += is_sib(v) ? 0.0 : (double)q[v];
-          qsum = (float)block_reduce(part, OpSum(), 0.0, S.dscr);
+          qsum = (float)group_reduce<WB>(part, OpSum(), 0.0, S.dscr);
         }
         if (zero_nb) {
           if (P.static_zero_q) {
             for (int w = tid; w < ((ncols + 31) >> 5); w += NT) S.nbmask[w] = 0u;
-            __syncthreads();
+            WB::sync();
             for (int tt = tid; tt < kk1; tt += NT) {
               const int nbt = __ldg(nb_row + tt) + off - col0;
               if (nbt >= 0 && nbt < ncols) atomicOr(&S.nbmask[nbt >> 5], 1u << (nbt & 31));
@@ -671,7 +689,7 @@ __global__ void __launch_bounds__(LNE > 0 ? kLazyThreads : kWalkThreads) walk_ke
             }
           }
         }
-        __syncthreads();
+        WB::sync();
         const bool use_mask = zero_nb && P.static_zero_q;
         for (int e = tid; e < ncols; e += NT) {
           const int tkn = e + col0;
@@ -688,30 +706,50 @@ __global__ void __launch_bounds__(LNE > 0 ? kLazyThreads : kWalkThreads) walk_ke
         p_out = __fmul_rn(p_out, scale);
         scale = 1.0f;   // the subtraction pass stored normalised values
       } else {
+        // gtp[x] = 0 and, if the candidate was relaxed, gtp[its k+1 nearest] = 0; atomicExch hands every entry's old
+        // value to exactly one thread, whatever the table holds
         if (zero_nb) {
           for (int tt = tid; tt < kk1; tt += NT) {
             const int nbt = __ldg(nb_row + tt) + off - col0;
-            if (nbt >= 0 && nbt < ncols) S.p[nbt] = 0.f;
+            if (nbt >= 0 && nbt < ncols) removed += (double)atomicExch(&S.p[nbt], 0.f);
           }
         }
-        if (x >= col0 && x < col1) { if (tid == 0) S.p[x - col0] = 0.f; }
+        if (x >= col0 && x < col1) { if (tid == 0) removed += (double)atomicExch(&S.p[x - col0], 0.f); }
         else if (x == extra_tok) p_extra = 0.f;
       }
-      __syncthreads();
-      float part = 0.f;
-      for (int e = tid; e < ncols; e += NT) part += S.p[e];
-      double tot = block_reduce((double)part, OpSum(), 0.0, S.dscr);
-      tot += (double)p_extra + (double)p_out * (double)(V - ncols - (extra_tok >= 0 ? 1 : 0));
+      double tot;
+      bool resum = cfg.static_tree || !win_tot_valid;
+      if (!resum) {
+        // one barrier: per-warp partials of the removed mass (double-buffered by rejection parity), summed by everyone
+        removed = warp_reduce(removed, OpSum());
+        double* rs = rsum + (rej_parity & 1) * 32;
+        ++rej_parity;
+        if ((tid & 31) == 0) rs[tid >> 5] = removed;
+        WB::sync();
+        double rem = 0.0;
+        for (int w = 0; w < (NT >> 5); ++w) rem += rs[w];
+        win_tot -= rem;
+        if (win_tot < 1e-6) resum = true;     // nearly everything is gone: take the exact sum (the == 0 test below)
+      }
+      if (resum) {
+        WB::sync();
+        float part = 0.f;
+        for (int e = tid; e < ncols; e += NT) part += S.p[e];
+        win_tot = group_reduce<WB>((double)part, OpSum(), 0.0, S.dscr);
+        win_tot_valid = !cfg.static_tree;
+      }
+      tot = win_tot + (double)p_extra + (double)p_out * (double)(V - ncols - (extra_tok >= 0 ? 1 : 0));
       if ((float)tot == 0.f) {   // gtp = ones_like(gtp)
         for (int e = tid; e < ncols; e += NT) S.p[e] = 1.0f;
         if (extra_tok >= 0) p_extra = 1.0f;
         p_out = 1.0f;
         tot = (double)V;
+        win_tot = (double)ncols;
         out_flags |= LANTERN_OUT_UNIFORM_FALLBACK;
+        WB::sync();
       }
       scale = __fdiv_rn(1.0f, (float)tot);   // gtp /= gtp.sum(), applied lazily
       adjust = true;
-      __syncthreads();
     }
   }
 
@@ -722,9 +760,11 @@ __global__ void __launch_bounds__(LNE > 0 ? kLazyThreads : kWalkThreads) walk_ke
   } else {
     int node = S.ri[best * D + accept_length - 1];
     if (node < 0) node += T;
-    set_distribution(node, P.tail_raw != 0);
+    // the distribution of the last accepted node is often still in place, untouched (it was made for a level that had
+    // no children to try): the reference recomputes the same softmax (:784-786)
+    if (!(dist_node == node && !dist_dirty && dist_raw == (P.tail_raw != 0))) set_distribution(node, P.tail_raw != 0);
   }
-  __syncthreads();
+  WB::sync();
 
   // ---------------- bonus token: inverse CDF, fp64, index order ----------------
   const float u = (cfg.bonus_uniform_last && P.in.uniforms)
@@ -748,15 +788,15 @@ __global__ void __launch_bounds__(LNE > 0 ? kLazyThreads : kWalkThreads) walk_ke
     if (S.p[i] > 0.f) last_nz = i;
   }
   double wtot;
-  const double incl = block_scan_incl(loc, S.dscr, &wtot);
+  const double incl = block_scan_incl<WB>(loc, S.dscr, &wtot);
   const double massA = (double)p_out * (double)col0;
   const int n_suffix_uniform = V - col1 - ((extra_tok >= col1) ? 1 : 0);
   const double massB = (double)p_extra + (double)p_out * (double)n_suffix_uniform;
   const double total = massA + wtot + massB;
   const double target = (double)u * total;
-  __syncthreads();
+  WB::sync();
   if (tid == 0) { S.iscr[36] = 0x7fffffff; S.iscr[37] = -1; }
-  __syncthreads();
+  WB::sync();
   {
     double run = massA + incl - loc;
     if (target >= run && target < run + loc) {
@@ -767,7 +807,7 @@ __global__ void __launch_bounds__(LNE > 0 ? kLazyThreads : kWalkThreads) walk_ke
     }
     if (last_nz >= 0) atomicMax(&S.iscr[37], last_nz + col0);
   }
-  __syncthreads();
+  WB::sync();
   int token = S.iscr[36];
   if (token == 0x7fffffff) {
     if (target < massA && p_out > 0.f) {
@@ -818,6 +858,7 @@ static size_t walk_smem_bytes(const lantern_accept_cfg& c, int lazy_ne, bool spi
   o += (size_t)((c.n_rows + 4) & ~3) * 4;
   o += kMaxSib * 4 + 36 * 4 + 40 * 4;
   o += (size_t)((c.n_paths + 3) & ~3) * 4 + 16;
+  o += 2 * 32 * 8 + 8;
   return o;
 }
 

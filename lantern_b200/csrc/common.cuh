@@ -240,15 +240,18 @@ __device__ __forceinline__ T block_reduce(T v, Op op, T identity, T* scratch) {
 struct BlockBar {
   static __device__ __forceinline__ void sync() { __syncthreads(); }
   static __device__ __forceinline__ int size() { return (int)blockDim.x; }
+  static __device__ __forceinline__ int tid() { return (int)threadIdx.x; }
 };
-template <int ID, int N>
+// threads OFF .. OFF + N - 1 of the CTA (a multiple of 32 each) behind named barrier ID
+template <int ID, int N, int OFF = 0>
 struct NamedBar {
   static __device__ __forceinline__ void sync() { asm volatile("bar.sync %0, %1;" ::"n"(ID), "n"(N) : "memory"); }
   static __device__ __forceinline__ int size() { return N; }
+  static __device__ __forceinline__ int tid() { return (int)threadIdx.x - OFF; }
 };
 template <class Bar, typename T, typename Op>
 __device__ __forceinline__ T group_reduce(T v, Op op, T identity, T* scratch) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = (Bar::size() + 31) >> 5;
+  const int lane = Bar::tid() & 31, warp = Bar::tid() >> 5, nwarp = (Bar::size() + 31) >> 5;
   v = warp_reduce(v, op);
   Bar::sync();  // protect scratch from a previous use
   if (lane == 0) scratch[warp] = v;
@@ -278,16 +281,17 @@ struct OpMaxI {
 
 // Block-wide scan of doubles: returns this thread's inclusive prefix, *total gets the block sum.
 // `scratch` holds one double per warp (<= 32 warps).
+template <class Bar = BlockBar>
 __device__ __forceinline__ double block_scan_incl(double v, double* scratch, double* total) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = (blockDim.x + 31) >> 5;
+  const int lane = Bar::tid() & 31, warp = Bar::tid() >> 5, nwarp = (Bar::size() + 31) >> 5;
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) {
     const double n = __shfl_up_sync(0xffffffffu, v, o);
     if (lane >= o) v += n;
   }
-  __syncthreads();
+  Bar::sync();
   if (lane == 31) scratch[warp] = v;
-  __syncthreads();
+  Bar::sync();
   // every warp scans the warp totals itself (no second barrier)
   double t = lane < nwarp ? scratch[lane] : 0.0;
 #pragma unroll

@@ -38,7 +38,7 @@ template <int NE, class Bar = BlockBar>
 __device__ __forceinline__ uint32_t radix_select_kth(const float (&s)[NE], int k, unsigned* hist /*[258]*/) {
   uint32_t prefix = 0, mask = 0;
   int krem = k;
-  const int tid = threadIdx.x;
+  const int tid = Bar::tid();
 #pragma unroll 1
   for (int shift = 24; shift >= 0; shift -= 8) {
     for (int i = tid; i < 256; i += Bar::size()) hist[i] = 0;
@@ -122,7 +122,7 @@ __device__ __forceinline__ void count_fields(const float (&s)[NE], const Classif
     const unsigned od = ((j < 4 ? o_lo : o_hi) >> ((j & 3) * 8)) & 0xffu;
     w[j] = ev | (od << 16);
   }
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = Bar::size() >> 5;
+  const int lane = Bar::tid() & 31, warp = Bar::tid() >> 5, nwarp = Bar::size() >> 5;
 #pragma unroll
   for (int j = 0; j < 8; ++j) w[j] = __reduce_add_sync(0xffffffffu, w[j]);   // 32 lanes * 255 < 65536: no carry
   Bar::sync();   // previous readers of sm.total / warp_cnt are done
@@ -131,8 +131,8 @@ __device__ __forceinline__ void count_fields(const float (&s)[NE], const Classif
     for (int j = 0; j < 8; ++j) sm.warp_cnt[warp][j] = w[j];
   }
   Bar::sync();
-  if (threadIdx.x < 32) {
-    const int f = threadIdx.x & 15;
+  if (Bar::tid() < 32) {
+    const int f = Bar::tid() & 15;
     unsigned tot = 0;
     for (int wi = 0; wi < nwarp; ++wi) tot += (sm.warp_cnt[wi][f >> 1] >> ((f & 1) * 16)) & 0xffffu;
     // suffix sums over the 16 fields (lanes 16..31 mirror lanes 0..15): above = sum of counts of higher fields
@@ -143,7 +143,7 @@ __device__ __forceinline__ void count_fields(const float (&s)[NE], const Classif
       if (f + o < 16) incl += n;
     }
     const unsigned above = incl - tot;
-    if (threadIdx.x < 16 && above < (unsigned)k && above + tot >= (unsigned)k) {
+    if (Bar::tid() < 16 && above < (unsigned)k && above + tot >= (unsigned)k) {
       sm.i_scr[1] = f; sm.i_scr[2] = (int)above; sm.i_scr[3] = (int)tot;
     }
   }
@@ -153,7 +153,7 @@ __device__ __forceinline__ void count_fields(const float (&s)[NE], const Classif
 // Exact krem-th largest (1-based) of sm.list[0..m): one warp per candidate, lanes split the comparisons.
 template <class Bar = BlockBar>
 __device__ __forceinline__ float rank_list(int m, int krem, SelectSmem& sm) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = Bar::size() >> 5;
+  const int lane = Bar::tid() & 31, warp = Bar::tid() >> 5, nwarp = Bar::size() >> 5;
   for (int i = warp; i < m; i += nwarp) {
     const float vi = sm.list[i];
     int gt = 0, ge = 0;
@@ -185,30 +185,20 @@ __device__ __forceinline__ Classifier64 make_classifier64(float lo, float hi) {
   return c;
 }
 
-// Tier 1.  `buf` is a [NE][NT] float array in shared memory (column tid is private to the thread).
+// Tier 1, second half: everything after the parking pass.  Every thread of the group passes its count of elements
+// above the bracket and the number of elements it parked in its column of `buf` ([slots][NT], column Bar::tid()).
 // Returns true and sets *result when the k-th largest value was found.
-template <int NE, int NT>
-__device__ __forceinline__ bool bracket_select(const float (&s)[NE], int k, float lo, float hi, float* buf,
+template <int NT, class Bar = BlockBar>
+__device__ __forceinline__ bool bracket_finish(int above, int slot, int k, float lo, float hi, float* buf,
                                                SelectSmem& sm, float* result) {
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tid = Bar::tid(), lane = tid & 31, warp = tid >> 5;
   constexpr int NW = NT / 32;
-  int above = 0, slot = 0;
-#pragma unroll
-  for (int e = 0; e < NE; ++e) {
-    const float v = s[e];
-    const bool ab = v > hi;
-    above += ab;
-    if (!ab && v >= lo) {
-      buf[slot * NT + tid] = v;
-      ++slot;
-    }
-  }
-  // block totals of `above` and `slot`
+  // group totals of `above` and `slot`
   const int wa = __reduce_add_sync(0xffffffffu, above), wi = __reduce_add_sync(0xffffffffu, slot);
-  __syncthreads();
+  Bar::sync();
   if (lane == 0) { sm.warp_cnt[warp][0] = (unsigned)wa; sm.warp_cnt[warp][1] = (unsigned)wi; }
   if (tid < 64) sm.hist64[tid] = 0u;
-  __syncthreads();
+  Bar::sync();
   int tot_above = 0, tot_in = 0;
 #pragma unroll
   for (int w = 0; w < NW; ++w) { tot_above += (int)sm.warp_cnt[w][0]; tot_in += (int)sm.warp_cnt[w][1]; }
@@ -219,7 +209,7 @@ __device__ __forceinline__ bool bracket_select(const float (&s)[NE], int k, floa
     const Classifier64 cls = make_classifier64(lo, hi);
     if (!isfinite(cls.scale) || !isfinite(cls.bias23)) return false;
     for (int i = 0; i < slot; ++i) atomicAdd(&sm.hist64[cls(buf[i * NT + tid])], 1u);
-    __syncthreads();
+    Bar::sync();
     if (warp == 0) {
       // lane l owns fields 2l, 2l+1; suffix sums from the top field down
       const unsigned c0 = sm.hist64[2 * lane], c1 = sm.hist64[2 * lane + 1];
@@ -237,7 +227,7 @@ __device__ __forceinline__ bool bracket_select(const float (&s)[NE], int k, floa
       }
       if (lane == 0) sm.i_scr[0] = 0;
     }
-    __syncthreads();
+    Bar::sync();
     const unsigned F = (unsigned)sm.i_scr[1];
     const int above2 = sm.i_scr[2], cntF = sm.i_scr[3];
     if (cntF <= kListMax) {
@@ -245,8 +235,8 @@ __device__ __forceinline__ bool bracket_select(const float (&s)[NE], int k, floa
         const float v = buf[i * NT + tid];
         if (cls(v) == F) sm.list[atomicAdd(&sm.i_scr[0], 1)] = v;
       }
-      __syncthreads();
-      *result = rank_list(cntF, krem - above2, sm);
+      Bar::sync();
+      *result = rank_list<Bar>(cntF, krem - above2, sm);
       return true;
     }
     // too many candidates (ties / dense bracket): shrink to the exact [min, max] of field F and repeat
@@ -255,14 +245,34 @@ __device__ __forceinline__ bool bracket_select(const float (&s)[NE], int k, floa
       const float v = buf[i * NT + tid];
       if (cls(v) == F) { mn = fminf(mn, v); mxv = fmaxf(mxv, v); }
     }
-    mn = -block_reduce(-mn, OpMaxF(), -INFINITY, sm.f4[0]);
-    mxv = block_reduce(mxv, OpMaxF(), -INFINITY, sm.f4[1]);
+    mn = -group_reduce<Bar>(-mn, OpMaxF(), -INFINITY, sm.f4[0]);
+    mxv = group_reduce<Bar>(mxv, OpMaxF(), -INFINITY, sm.f4[1]);
     if (mn == mxv) { *result = mn; return true; }
     lo = mn; hi = mxv;
     if (tid < 64) sm.hist64[tid] = 0u;
-    __syncthreads();
+    Bar::sync();
   }
   return false;
+}
+
+// Tier 1.  `buf` is a [NE][NT] float array in shared memory (column tid is private to the thread).
+// Returns true and sets *result when the k-th largest value was found.
+template <int NE, int NT, class Bar = BlockBar>
+__device__ __forceinline__ bool bracket_select(const float (&s)[NE], int k, float lo, float hi, float* buf,
+                                               SelectSmem& sm, float* result) {
+  const int tid = Bar::tid();
+  int above = 0, slot = 0;
+#pragma unroll
+  for (int e = 0; e < NE; ++e) {
+    const float v = s[e];
+    const bool ab = v > hi;
+    above += ab;
+    if (!ab && v >= lo) {
+      buf[slot * NT + tid] = v;
+      ++slot;
+    }
+  }
+  return bracket_finish<NT, Bar>(above, slot, k, lo, hi, buf, sm, result);
 }
 
 // k-th largest of the row held in s[] (NE per thread, padded slots = -inf), 1 <= k <= number of slots.
@@ -270,7 +280,7 @@ __device__ __forceinline__ bool bracket_select(const float (&s)[NE], int k, floa
 template <int NE, class Bar = BlockBar>
 __device__ __forceinline__ bool select_kth_largest(const float (&s)[NE], int k, float row_min, float row_max,
                                                 SelectSmem& sm, float* out) {
-  const int tid = threadIdx.x;
+  const int tid = Bar::tid();
   bool ok = isfinite(row_min) && isfinite(row_max);
   float lo = row_min, hi = row_max;
   float result = 0.f;

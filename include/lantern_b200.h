@@ -193,6 +193,27 @@ LANTERN_API int lantern_tree_from_candidates(const int64_t* cand_dev, const int6
                                              int32_t* retrieve32_dev, void* stream);
 
 /*
+ * Single-prompt drop-in call (the reference's batch-1 evaluate_posterior(logits, candidates, ...),
+ * ea_model_llamagen.py:709 / :464, ea_model_lumina_mgpt.py:610, drafters/utils.py:333): one entry that uploads the
+ * step's uniforms, rebuilds the tree inputs from `candidates` / `retrieve_indices` (lantern_tree_from_candidates),
+ * runs the fused step with the automatic schedule, reads the results back and synchronises `stream` once.
+ * The context owns small staging buffers (pinned host + device, allocated by lantern_call_create for trees of up to
+ * max_rows nodes and max_cells = n_paths * depth path cells); one context per host thread and device.
+ * Uniforms: write n_uniforms values into lantern_call_uniforms(h) before the call (n_uniforms = 0: device Philox
+ * stream of cfg).  cfg->n_items must be 1; in->tree_tokens / retrieve / uniforms are ignored.
+ * out_host[5 + 2*depth] = {accept_length, best_candidate, token, n_draws, flags, path_tokens[depth],
+ * select_indices[depth]}.  sample_p_dev: [vocab] fp32 or NULL.
+ */
+typedef struct lantern_call lantern_call;
+LANTERN_API int lantern_call_create(int32_t max_rows, int32_t max_cells, lantern_call** out);
+LANTERN_API void lantern_call_destroy(lantern_call* h);
+LANTERN_API float* lantern_call_uniforms(lantern_call* h);
+LANTERN_API int lantern_posterior_call(lantern_call* h, const lantern_accept_cfg* cfg, const lantern_accept_in* in,
+                                       const int64_t* cand_dev, const int64_t* retrieve_dev, int32_t n_uniforms,
+                                       float* sample_p_dev, void* workspace_dev, size_t workspace_bytes,
+                                       int32_t* out_host, void* stream);
+
+/*
  * Bonus-token draw from caller-supplied probability rows (update_inference_inputs given a
  * sample_p that did not come from lantern_accept_fused): token[b] = min{i : cdf_i > u[b] * total}.
  * Replaces torch.multinomial(prob, 1) at ea_model_llamagen.py:978, ea_model_lumina_mgpt.py:781.

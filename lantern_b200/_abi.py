@@ -22,7 +22,8 @@ EXPORTS = (
     "lantern_version", "lantern_last_error", "lantern_accept_workspace_bytes", "lantern_accept_fused",
     "lantern_accept_phases",
     "lantern_sample_tokens", "lantern_kv_compact", "lantern_build_neighbors", "lantern_philox_uniforms",
-    "lantern_session_create", "lantern_session_step", "lantern_session_destroy", "lantern_debug_dist_gemm", "lantern_build_neighbors_workspace_bytes", "lantern_build_dynamic_tree", "lantern_draft_sample",
+    "lantern_session_create", "lantern_session_step", "lantern_session_destroy", "lantern_debug_dist_gemm", "lantern_build_neighbors_workspace_bytes", "lantern_call_create", "lantern_call_destroy",
+    "lantern_call_uniforms", "lantern_posterior_call", "lantern_build_dynamic_tree", "lantern_draft_sample",
     "lantern_tree_from_candidates", "lantern_session_last_route", "lantern_accept_greedy",
     "lantern_accept_greedy_workspace_bytes",
 )
@@ -114,6 +115,15 @@ def load() -> C.CDLL:
                                             C.c_size_t, C.c_void_p, C.c_void_p]
     lib.lantern_build_neighbors_workspace_bytes.restype = C.c_size_t
     lib.lantern_build_neighbors_workspace_bytes.argtypes = [C.c_int32, C.c_int32, C.c_int32]
+    lib.lantern_call_create.restype = C.c_int
+    lib.lantern_call_create.argtypes = [C.c_int32, C.c_int32, C.POINTER(C.c_void_p)]
+    lib.lantern_call_destroy.restype = None
+    lib.lantern_call_destroy.argtypes = [C.c_void_p]
+    lib.lantern_call_uniforms.restype = C.c_void_p
+    lib.lantern_call_uniforms.argtypes = [C.c_void_p]
+    lib.lantern_posterior_call.restype = C.c_int
+    lib.lantern_posterior_call.argtypes = [C.c_void_p, C.POINTER(AcceptCfg), C.POINTER(AcceptIn), C.c_void_p, C.c_void_p,
+                                           C.c_int32, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]
     lib.lantern_debug_dist_gemm.restype = C.c_int
     lib.lantern_debug_dist_gemm.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p]
     lib.lantern_draft_sample.restype = C.c_int

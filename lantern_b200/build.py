@@ -15,7 +15,7 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(PKG)
 CSRC = os.path.join(PKG, "csrc")
 LIB = os.path.join(PKG, "liblantern_b200.so")
-SOURCES = ["abi.cu", "accept.cu", "sample.cu", "kv_compact.cu", "neighbors.cu", "neighbors_tc.cu", "session.cu", "dyntree.cu", "draft_sample.cu", "greedy.cu"]
+SOURCES = ["abi.cu", "accept.cu", "sample.cu", "kv_compact.cu", "neighbors.cu", "neighbors_tc.cu", "session.cu", "dyntree.cu", "draft_sample.cu", "greedy.cu", "call.cu"]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr",
               "-Xptxas", "-v"]

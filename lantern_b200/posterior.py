@@ -205,6 +205,23 @@ class _HostIO:
         self.u_dev = torch.empty(4096, dtype=torch.float32, device=device)
         self.r_host = torch.zeros(8, dtype=torch.int32).pin_memory()
         self.r_np = self.r_host.numpy()
+        # context of lantern_posterior_call (the one-FFI-call form of a batch-1 evaluate_posterior)
+        self.call = None
+        self.call_u = None
+        self.call_out = np.zeros(5 + 2 * 64, dtype=np.int32)
+
+    MAX_ROWS, MAX_CELLS = 1024, 16384
+
+    def call_handle(self):
+        if self.call is None:
+            import ctypes as C
+            lib = _abi.load()
+            h = C.c_void_p()
+            _abi.check(lib.lantern_call_create(self.MAX_ROWS, self.MAX_CELLS, C.byref(h)))
+            self.call = h
+            ptr = lib.lantern_call_uniforms(h)
+            self.call_u = np.ctypeslib.as_array((C.c_float * (self.MAX_ROWS + 1)).from_address(ptr))
+        return self.call
 
 
 _host_io = {}
@@ -269,11 +286,78 @@ def _verify_greedy(fam: FamilySpec, logits, candidates: torch.Tensor, lantern=Fa
     return res.best_candidate[0].long(), res.accept_length[0].long(), row
 
 
+def _verify_one_call(fam: FamilySpec, logits: "TreeLogits", candidates: torch.Tensor, temp, top_p, top_k, lantern,
+                     lantern_k, lantern_delta, nearest_latents, static_inputs, rng, philox, want_sample_p):
+    """The fused-handle form of ``_verify`` behind ONE FFI call (``lantern_posterior_call``): uniforms upload, tree inputs
+    from ``candidates`` / ``retrieve_indices``, the fused step, the result read-back and the stream synchronisation all
+    happen inside the library.  Same results as the tensor-by-tensor route below."""
+    import ctypes as C
+    device = logits.device
+    cond, uncond = logits.cond, logits.uncond
+    cand = candidates
+    if cand.device != device or cand.dtype != torch.int64 or not cand.is_contiguous():
+        cand = cand.to(device=device, dtype=torch.int64).contiguous()
+    ri64 = logits.retrieve_indices
+    if ri64.device != device or ri64.dtype != torch.int64 or not ri64.is_contiguous():
+        ri64 = ri64.to(device=device, dtype=torch.int64).contiguous()
+    L, D = cand.shape
+    T = cond.shape[1]
+    if fam.family_id == _abi.FAMILY_LUMINA and logits.top_k is not None:
+        top_k = logits.top_k
+    table, k = None, int(lantern_k)
+    if lantern:
+        k = min(k, fam.ncols - 1)
+        table = device_table(nearest_latents, device, min(k + 1, fam.ncols - 1))
+    static = static_inputs[0] if static_inputs is not None else None
+    ver = _get_verifier(fam, temp, top_p, top_k, logits.cfg_scale, lantern, k, lantern_delta, table, static, device)
+    io = _io(device)
+    handle = io.call_handle()
+    n_u, state = 0, None
+    if rng == "python":
+        state, u = _draw_python_uniforms(T)
+        io.call_u[:T] = u                                   # float64 -> float32, round to nearest like torch
+        io.call_u[T] = float(torch.rand(()).item())         # bonus draw (see _verify for the RNG-state note)
+        n_u = T + 1
+    cfg, need = ver.cached_cfg(1, T, L, D, cond, False, n_u, philox, rng == "python")
+    ain = _abi.AcceptIn()
+    ain.logits_cond, ain.logits_uncond = cond.data_ptr(), (uncond.data_ptr() if uncond is not None else None)
+    ain.row_kinds = logits.row_kinds.data_ptr() if logits.row_kinds is not None else None
+    ain.nbr_table = ver.nbr_table.data_ptr() if ver.nbr_table is not None else None
+    keep = None
+    if static_inputs is not None:
+        st, node_q, draft_op, sib_tokens = static_inputs
+        ain.node_q, ain.draft_op = node_q.data_ptr(), draft_op.data_ptr()
+        ain.node_qrow, ain.sib_off, ain.sib_idx = st.node_qrow.data_ptr(), st.sib_off.data_ptr(), st.sib_idx.data_ptr()
+        ain.sib_tokens, ain.sib_tokens_stride = sib_tokens.data_ptr(), sib_tokens.stride(0)
+        keep = static_inputs
+    sample_p = torch.empty(cond.shape[-1], dtype=torch.float32, device=device) if want_sample_p else None
+    work = ver.workspace(need, device)
+    out = io.call_out
+    _abi.check(ver.lib.lantern_posterior_call(handle, C.byref(cfg), C.byref(ain), cand.data_ptr(), ri64.data_ptr(), n_u,
+                                              sample_p.data_ptr() if sample_p is not None else None, work.data_ptr(),
+                                              work.numel(), out.ctypes.data,
+                                              torch.cuda.current_stream(device).cuda_stream))
+    a, best, token, draws = int(out[0]), int(out[1]), int(out[2]), int(out[3])
+    if state is not None:                                    # advance the module RNG exactly like the reference
+        random.setstate(state)
+        for _ in range(draws - 1):
+            random.random()
+    if sample_p is None:
+        sample_p = torch.empty(0, device=device)
+    sample_p._lantern_token = token
+    del keep
+    return torch.tensor(best), a, sample_p
+
+
 def _verify(fam: FamilySpec, logits, candidates: torch.Tensor, *, temp=1.0, top_p=1.0, top_k=0, lantern=False,
             lantern_k=1000, lantern_delta=0.1, nearest_latents=None, static_inputs=None, rng="python",
             philox=(0, 0), want_sample_p=True):
     """Returns (best_candidate 0-d int64 CPU tensor, accept_length int, sample_p [V] with ``_lantern_token``)."""
     device = logits.device
+    if (isinstance(logits, TreeLogits) and logits.cond.shape[0] == 1 and logits.cond.shape[1] <= _HostIO.MAX_ROWS
+            and candidates.numel() <= _HostIO.MAX_CELLS and candidates.shape[1] <= 64):
+        return _verify_one_call(fam, logits, candidates, temp, top_p, top_k, lantern, lantern_k, lantern_delta,
+                                nearest_latents, static_inputs, rng, philox, want_sample_p)
     stream = torch.cuda.current_stream(device)
     cond, uncond, cfg_scale, tokens, retrieve, kinds, T, lumina_top_k = _tree_inputs(logits, candidates, stream)
     if fam.family_id == _abi.FAMILY_LUMINA and lumina_top_k is not None:

@@ -146,6 +146,27 @@ class Verifier:
         c.philox_seed, c.philox_step = int(philox[0]) & (2**64 - 1), int(philox[1]) & (2**64 - 1)
         return c
 
+    def cached_cfg(self, B, T, L, D, logits: torch.Tensor, shared: bool, n_uni: int, philox=(0, 0),
+                   bonus_uniform_last: bool = False):
+        """(lantern_accept_cfg, workspace bytes) for a launch shape; the struct is cached per shape and only its per-call
+        fields are refreshed."""
+        ckey = (B, T, L, D, logits.dtype, logits.stride(0), logits.stride(1), shared, n_uni)
+        cached = self._cfg_cache.get(ckey)
+        if cached is None:
+            cfg = self._cfg(B, T, L, D, logits, shared, n_uni, philox)
+            if len(self._cfg_cache) > 32:
+                self._cfg_cache.clear()
+            cached = self._cfg_cache[ckey] = (cfg, int(self.lib.lantern_accept_workspace_bytes(C.byref(cfg))))
+        cfg, need = cached
+        cfg.philox_seed, cfg.philox_step = int(philox[0]) & (2**64 - 1), int(philox[1]) & (2**64 - 1)
+        cfg.bonus_uniform_last = int(bonus_uniform_last)
+        return cfg, need
+
+    def workspace(self, need: int, dev) -> torch.Tensor:
+        if self._work is None or self._work.numel() < need or self._work.device != dev:
+            self._work = torch.empty(max(need, 1), dtype=torch.uint8, device=dev)
+        return self._work
+
     def step(self, logits_cond: torch.Tensor, logits_uncond: Optional[torch.Tensor], tree_tokens: torch.Tensor,
              retrieve: Optional[torch.Tensor] = None, *, row_kinds: Optional[torch.Tensor] = None,
              uniforms: Optional[torch.Tensor] = None, philox: Tuple[int, int] = (0, 0),
@@ -179,16 +200,7 @@ class Verifier:
             if uniforms.dtype != torch.float32 or not uniforms.is_contiguous() or uniforms.shape[0] != B:
                 raise ValueError("uniforms must be contiguous fp32 [B, n]")
             n_uni = uniforms.shape[1]
-        ckey = (B, T, L, D, logits_cond.dtype, logits_cond.stride(0), logits_cond.stride(1), shared, n_uni)
-        cached = self._cfg_cache.get(ckey)
-        if cached is None:
-            cfg = self._cfg(B, T, L, D, logits_cond, shared, n_uni, philox)
-            if len(self._cfg_cache) > 32:
-                self._cfg_cache.clear()
-            cached = self._cfg_cache[ckey] = (cfg, int(self.lib.lantern_accept_workspace_bytes(C.byref(cfg))))
-        cfg, need = cached
-        cfg.philox_seed, cfg.philox_step = int(philox[0]) & (2**64 - 1), int(philox[1]) & (2**64 - 1)
-        cfg.bonus_uniform_last = int(bonus_uniform_last)
+        cfg, need = self.cached_cfg(B, T, L, D, logits_cond, shared, n_uni, philox, bonus_uniform_last)
         ain = _abi.AcceptIn()
         ain.logits_cond, ain.logits_uncond = _ptr(logits_cond), _ptr(logits_uncond)
         ain.tree_tokens, ain.retrieve = _ptr(tree_tokens), _ptr(retrieve)
@@ -219,8 +231,7 @@ class Verifier:
         aout.accept_length, aout.best_candidate, aout.token = _ptr(res.accept_length), _ptr(res.best_candidate), _ptr(res.token)
         aout.path_tokens, aout.select_indices = _ptr(res.path_tokens), _ptr(res.select_indices)
         aout.n_draws, aout.flags, aout.sample_p = _ptr(res.n_draws), _ptr(res.flags), _ptr(res.sample_p)
-        if self._work is None or self._work.numel() < need or self._work.device != dev:
-            self._work = torch.empty(max(need, 1), dtype=torch.uint8, device=dev)
+        self.workspace(need, dev)
         stream = torch.cuda.current_stream(dev).cuda_stream
         _abi.check(self.lib.lantern_accept_phases(C.byref(cfg), C.byref(ain), C.byref(aout), self._work.data_ptr(),
                                                   self._work.numel(), stream, phases))

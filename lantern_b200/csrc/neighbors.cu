@@ -5,6 +5,7 @@
 // all N rows are computed straight into shared memory from a transposed copy of the codebook (coalesced
 // reads), then the (distance, id) pairs are bitonic-sorted in shared memory and the first K ids written out.
 // The N x N distance matrix never touches HBM.
+#include <algorithm>
 #include <cstdlib>
 
 #include "common.cuh"
@@ -21,17 +22,28 @@ __global__ void transpose_kernel(const float* __restrict__ E, float* __restrict_
   }
 }
 
-// row_redo != NULL: only the rows the tensor-core route marked are computed (the others already hold their result).
+// Rows the tensor-core route marked, gathered into a list (order is irrelevant).
+__global__ void nbr_redo_list_kernel(const unsigned char* __restrict__ row_redo, int N, int* __restrict__ list,
+                                     int* __restrict__ count) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < N; i += gridDim.x * blockDim.x)
+    if (row_redo[i]) list[atomicAdd(count, 1)] = i;
+}
+
+// Persistent CTAs: every row (redo_list == NULL) or only the listed rows (none in the common case: the CTAs exit at once).
 __global__ void __launch_bounds__(kNbrThreads) nbr_rows_kernel(const float* __restrict__ E,
                                                                const float* __restrict__ Et, int N, int d, int K,
                                                                int NP /*pow2 >= N*/, int32_t* __restrict__ out,
-                                                               const unsigned char* __restrict__ row_redo) {
+                                                               const int* __restrict__ redo_list,
+                                                               const int* __restrict__ redo_count) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double* key = reinterpret_cast<double*>(smem_raw);
   int* idx = reinterpret_cast<int*>(smem_raw + (size_t)NP * 8);
   float* er = reinterpret_cast<float*>(smem_raw + (size_t)NP * 12);
-  const int r = blockIdx.x, tid = threadIdx.x;
-  if (row_redo != nullptr && row_redo[r] == 0) return;
+  const int tid = threadIdx.x;
+  const int n_work = redo_list ? *redo_count : N;
+  for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
+  const int r = redo_list ? redo_list[w] : w;
+  __syncthreads();   // the previous row's readers of the shared arrays are done
   for (int c = tid; c < d; c += kNbrThreads) er[c] = E[(int64_t)r * d + c];
   __syncthreads();
   for (int c = tid; c < NP; c += kNbrThreads) {
@@ -68,6 +80,7 @@ __global__ void __launch_bounds__(kNbrThreads) nbr_rows_kernel(const float* __re
     }
   }
   for (int c = tid; c < K; c += kNbrThreads) out[(int64_t)r * K + c] = idx[c];
+  }
 }
 
 }  // namespace lantern
@@ -75,7 +88,7 @@ __global__ void __launch_bounds__(kNbrThreads) nbr_rows_kernel(const float* __re
 bool neighbors_tc_eligible(int N, int d, int K);
 size_t neighbors_tc_workspace_bytes(int N, int d);
 int build_neighbors_tensor_core(const float* E_dev, int N, int d, int K, int32_t* out_dev, void* workspace,
-                                unsigned char** row_redo_out, int** flags_out, cudaStream_t s);
+                                unsigned char** row_redo_out, int** flags_out, int** redo_list_out, cudaStream_t s);
 
 // route_dev[0] = 1: every row came from the tensor-core route; 2: the exact kernel computed some (or all) rows;
 // route_dev[1] = rows the exact kernel computed.
@@ -117,12 +130,12 @@ extern "C" int lantern_build_neighbors(const float* E_dev, int32_t N, int32_t d,
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   float* Et = static_cast<float*>(workspace_dev);
   unsigned char* redo = nullptr;
-  int* flags = nullptr;
+  int *flags = nullptr, *redo_list = nullptr;
   const bool tc = use_tc(N, d, K);
   if (tc) {   // tensor-core candidates + exact re-rank (bit-identical results); rows it cannot finish are marked
     const int rc = build_neighbors_tensor_core(E_dev, N, d, K, out_dev,
                                                static_cast<unsigned char*>(workspace_dev) + exact_bytes(N, d), &redo,
-                                               &flags, s);
+                                               &flags, &redo_list, s);
     if (rc != LANTERN_OK) return rc;
   }
   // exact kernel: every row (no tensor-core route for this shape) or the marked rows only (the other CTAs exit at once)
@@ -130,7 +143,9 @@ extern "C" int lantern_build_neighbors(const float* E_dev, int32_t N, int32_t d,
   transpose_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(E_dev, Et, N, d);
   if (smem > 48 * 1024)
     LANTERN_CUDA(cudaFuncSetAttribute(nbr_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  nbr_rows_kernel<<<N, kNbrThreads, smem, s>>>(E_dev, Et, N, d, K, NP, out_dev, redo);
+  if (tc) nbr_redo_list_kernel<<<kNumSMs, 256, 0, s>>>(redo, N, redo_list, flags + 2);
+  nbr_rows_kernel<<<std::min(N, kNumSMs), kNbrThreads, smem, s>>>(E_dev, Et, N, d, K, NP, out_dev, tc ? redo_list : nullptr,
+                                                                 tc ? flags + 2 : nullptr);
   if (route_dev) nbr_route_kernel<<<1, 1, 0, s>>>(flags, N, tc ? 1 : 0, route_dev);
   LANTERN_CUDA(cudaGetLastError());
   return LANTERN_OK;

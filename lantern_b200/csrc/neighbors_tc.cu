@@ -266,13 +266,82 @@ __global__ void __launch_bounds__(kGemmThreads) dist_gemm_kernel(const uint32_t*
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(2 * kTileN));
 }
 
+// Bitonic sort of EPT * kSelThreads (key, id) pairs, ascending by (key, id).  Element i = tid * EPT + e lives in a
+// register of thread tid: compare-exchange partners at distance j < EPT are in the same thread, at EPT <= j < 32 * EPT in
+// another lane of the warp (shuffles), beyond that in another warp (shared memory, two barriers).  For 2048 pairs that is
+// 10 shared-memory phases instead of the 66 of the all-shared-memory network.
+template <int EPT>
+__device__ __forceinline__ void bitonic_hybrid(double* __restrict__ key, int* __restrict__ idx) {
+  const int tid = threadIdx.x;
+  constexpr int NP = EPT * kSelThreads;
+  double k[EPT];
+  int ix[EPT];
+#pragma unroll
+  for (int e = 0; e < EPT; ++e) { k[e] = key[tid * EPT + e]; ix[e] = idx[tid * EPT + e]; }
+  __syncthreads();
+#pragma unroll 1
+  for (int size = 2; size <= NP; size <<= 1) {
+#pragma unroll 1
+    for (int j = size >> 1; j > 0; j >>= 1) {
+      if (j >= 32 * EPT) {                       // partner in another warp
+#pragma unroll
+        for (int e = 0; e < EPT; ++e) { key[tid * EPT + e] = k[e]; idx[tid * EPT + e] = ix[e]; }
+        __syncthreads();
+#pragma unroll
+        for (int e = 0; e < EPT; ++e) {
+          const int i = tid * EPT + e;
+          const double pk = key[i ^ j];
+          const int pix = idx[i ^ j];
+          const bool mine_gt = (k[e] > pk) || (k[e] == pk && ix[e] > pix);
+          const bool keep_min = ((i & j) == 0) == ((i & size) == 0);
+          if (mine_gt == keep_min) { k[e] = pk; ix[e] = pix; }
+        }
+        __syncthreads();
+      } else if (j >= EPT) {                     // partner in another lane
+        const int lx = j / EPT;
+#pragma unroll
+        for (int e = 0; e < EPT; ++e) {
+          const int i = tid * EPT + e;
+          const double pk = __shfl_xor_sync(0xffffffffu, k[e], lx);
+          const int pix = __shfl_xor_sync(0xffffffffu, ix[e], lx);
+          const bool mine_gt = (k[e] > pk) || (k[e] == pk && ix[e] > pix);
+          const bool keep_min = ((i & j) == 0) == ((i & size) == 0);
+          if (mine_gt == keep_min) { k[e] = pk; ix[e] = pix; }
+        }
+      } else {                                   // partner in the same thread
+#pragma unroll
+        for (int JJ = EPT >> 1; JJ > 0; JJ >>= 1) {
+          if (j == JJ) {
+#pragma unroll
+            for (int e = 0; e < EPT; ++e) {
+              if ((e & JJ) == 0) {
+                const int i = tid * EPT + e;
+                const bool up = (i & size) == 0;
+                const bool a_gt_b = (k[e] > k[e | JJ]) || (k[e] == k[e | JJ] && ix[e] > ix[e | JJ]);
+                if (a_gt_b == up) {
+                  const double tk = k[e]; k[e] = k[e | JJ]; k[e | JJ] = tk;
+                  const int ti = ix[e]; ix[e] = ix[e | JJ]; ix[e | JJ] = ti;
+                }
+              }
+            }
+          }
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int e = 0; e < EPT; ++e) { key[tid * EPT + e] = k[e]; idx[tid * EPT + e] = ix[e]; }
+  __syncthreads();
+}
+
 // One CTA per codebook row: exact top-K from the approximate distance row.
 template <int NE>
-__global__ void __launch_bounds__(kSelThreads) nbr_select_kernel(const float* __restrict__ E,
+__global__ void __launch_bounds__(kSelThreads, 2) nbr_select_kernel(const float* __restrict__ E,
                                                                  const float* __restrict__ norms,
                                                                  const float* __restrict__ Dapprox, int ld, int N,
                                                                  int d, int K, const float* __restrict__ max_norm_dev,
-                                                                 int32_t* __restrict__ out, int* __restrict__ flags,
+                                                                 float z_guess, int32_t* __restrict__ out,
+                                                                 int* __restrict__ flags,
                                                                  unsigned char* __restrict__ row_redo) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double* key = reinterpret_cast<double*>(smem_raw);                       // [kCandMax]
@@ -296,21 +365,35 @@ __global__ void __launch_bounds__(kSelThreads) nbr_select_kernel(const float* __
     v[4 * e4 + 2] = (j + 2 < N && j + 2 != r) ? -f.z : -INFINITY;
     v[4 * e4 + 3] = (j + 3 < N && j + 3 != r) ? -f.w : -INFINITY;
   }
-  float vmin = INFINITY, vmax = -INFINITY;
+  float vmin = INFINITY, vmax = -INFINITY, vsum = 0.f, vsq = 0.f;
 #pragma unroll
   for (int e = 0; e < NE; ++e) {
-    if (v[e] > -INFINITY) vmin = fminf(vmin, v[e]);
+    if (v[e] > -INFINITY) {
+      vmin = fminf(vmin, v[e]);
+      vsum += v[e];
+      vsq = fmaf(v[e], v[e], vsq);
+    }
     vmax = fmaxf(vmax, v[e]);
   }
   vmin = -block_reduce(-vmin, OpMaxF(), -INFINITY, sm.f4[2]);
   vmax = block_reduce(vmax, OpMaxF(), -INFINITY, sm.f4[3]);
+  vsum = block_reduce(vsum, OpSum(), 0.f, sm.f4[0]);
+  vsq = block_reduce(vsq, OpSum(), 0.f, sm.f4[1]);
   // tier 2/3 selectors expect finite extremes; -inf entries (self, padding) simply rank last
   float kth;
   {
     float tmp[NE];
 #pragma unroll
     for (int e = 0; e < NE; ++e) tmp[e] = v[e] > -INFINITY ? v[e] : vmin - 1.0f;
-    kth = select_slow<NE>(tmp, K, vmin - 1.0f, vmax, sm);
+    // First classification range: one standard deviation around the Gaussian guess of the K-th largest value instead
+    // of [min, max] - values outside fall into the two edge fields, and if the target is there the selector re-centres
+    // on that field's exact range, so any guess keeps the result exact; a good one saves one or two passes.
+    const float inv_n = 1.0f / (float)(N - 1);
+    const float mean = vsum * inv_n;
+    const float sd = sqrtf(fmaxf(vsq * inv_n - mean * mean, 0.f));
+    float lo = fmaxf(vmin - 1.0f, mean + (z_guess - 0.5f) * sd), hi = fminf(vmax, mean + (z_guess + 0.5f) * sd);
+    if (!(sd > 0.f) || !(lo < hi) || !isfinite(lo) || !isfinite(hi)) { lo = vmin - 1.0f; hi = vmax; }
+    kth = select_slow<NE>(tmp, K, lo, hi, sm);
   }
   // error bound of the TF32 cross term + fp32 norms (see header): |D~ - d^2| <= eps
   const float na = sqrtf(norms[r]);
@@ -396,17 +479,22 @@ __global__ void __launch_bounds__(kSelThreads) nbr_select_kernel(const float* __
     if (tid == 0) { atomicAdd(&flags[1], 1); row_redo[r] = 1; }
     return;
   }
-  for (int size = 2; size <= np; size <<= 1) {
-    for (int stride = size >> 1; stride > 0; stride >>= 1) {
-      for (int t = tid; t < (np >> 1); t += kSelThreads) {
-        const int lo = 2 * t - (t & (stride - 1)), hi = lo + stride;
-        const bool up = (lo & size) == 0;
-        const double ka = key[lo], kb = key[hi];
-        const int ia = cidx[lo], ib = cidx[hi];
-        const bool a_gt_b = (ka > kb) || (ka == kb && ia > ib);
-        if (a_gt_b == up) { key[lo] = kb; key[hi] = ka; cidx[lo] = ib; cidx[hi] = ia; }
+  if (np == 8 * kSelThreads) bitonic_hybrid<8>(key, cidx);
+  else if (np == 4 * kSelThreads) bitonic_hybrid<4>(key, cidx);
+  else if (np == 2 * kSelThreads) bitonic_hybrid<2>(key, cidx);
+  else {
+    for (int size = 2; size <= np; size <<= 1) {
+      for (int stride = size >> 1; stride > 0; stride >>= 1) {
+        for (int t = tid; t < (np >> 1); t += kSelThreads) {
+          const int lo = 2 * t - (t & (stride - 1)), hi = lo + stride;
+          const bool up = (lo & size) == 0;
+          const double ka = key[lo], kb = key[hi];
+          const int ia = cidx[lo], ib = cidx[hi];
+          const bool a_gt_b = (ka > kb) || (ka == kb && ia > ib);
+          if (a_gt_b == up) { key[lo] = kb; key[hi] = ka; cidx[lo] = ib; cidx[hi] = ia; }
+        }
+        __syncthreads();
       }
-      __syncthreads();
     }
   }
   for (int c = tid; c < K; c += kSelThreads) out[(size_t)r * K + c] = cidx[c];
@@ -428,7 +516,7 @@ static size_t align256(size_t x) { return (x + 255) & ~size_t(255); }
 
 // Scratch layout of the tensor-core route (all caller-owned, carved from one workspace).
 struct TcScratch {
-  size_t norms, mx, flags, redo, epk, D, total;
+  size_t norms, mx, flags, redo, redo_list, epk, D, total;
   int ld, dpad, Npad;
 };
 static TcScratch tc_scratch(int N, int d) {
@@ -441,6 +529,7 @@ static TcScratch tc_scratch(int N, int d) {
   t.mx = o;    o += 256;
   t.flags = o; o += 256;
   t.redo = o;  o += align256((size_t)N);
+  t.redo_list = o; o += align256((size_t)N * 4);
   t.epk = o;   o += align256((size_t)t.Npad * t.dpad * 4);
   t.D = o;     o += align256((size_t)N * t.ld * 4);
   t.total = o;
@@ -495,7 +584,7 @@ extern "C" LANTERN_API int lantern_debug_dist_gemm(const float* E_dev, int32_t N
 // finish (candidate overflow, violated error bound) are marked in row_redo for the exact kernel; nothing here
 // synchronises or allocates.  flags_dev[0..1] count those rows.
 int build_neighbors_tensor_core(const float* E_dev, int N, int d, int K, int32_t* out_dev, void* workspace,
-                                unsigned char** row_redo_out, int** flags_out, cudaStream_t s) {
+                                unsigned char** row_redo_out, int** flags_out, int** redo_list_out, cudaStream_t s) {
   const TcScratch t = tc_scratch(N, d);
   unsigned char* w = static_cast<unsigned char*>(workspace);
   float* norms = reinterpret_cast<float*>(w + t.norms);
@@ -509,10 +598,21 @@ int build_neighbors_tensor_core(const float* E_dev, int N, int d, int K, int32_t
   max_norm_kernel<<<1, 512, 0, s>>>(norms, N, mx);
   { int rc = launch_dist_gemm(E_dev, norms, N, d, Epk, D, t.ld, s); if (rc != LANTERN_OK) return rc; }
   const size_t sel_smem = (size_t)kCandMax * 12 + (size_t)kGemmMaxDim * 8;
+  // Gaussian guess (in standard deviations of the negated distance row) of the K-th largest of N - 1 values
+  float z_guess = 0.f;
+  {
+    const double p = (double)K / (double)(N - 1);
+    double zl = -8.0, zh = 8.0;
+    for (int it = 0; it < 60; ++it) {
+      const double zm = 0.5 * (zl + zh);
+      if (0.5 * erfc(zm / 1.4142135623730951) > p) zl = zm; else zh = zm;
+    }
+    z_guess = (float)(0.5 * (zl + zh));
+  }
   auto run_select = [&](auto kern) -> cudaError_t {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sel_smem);
     if (e != cudaSuccess) return e;
-    kern<<<N, kSelThreads, sel_smem, s>>>(E_dev, norms, D, t.ld, N, d, K, mx, out_dev, flags, redo);
+    kern<<<N, kSelThreads, sel_smem, s>>>(E_dev, norms, D, t.ld, N, d, K, mx, z_guess, out_dev, flags, redo);
     return cudaGetLastError();
   };
   if (N <= 8 * kSelThreads) LANTERN_CUDA(run_select(nbr_select_kernel<8>));
@@ -520,5 +620,6 @@ int build_neighbors_tensor_core(const float* E_dev, int N, int d, int K, int32_t
   else LANTERN_CUDA(run_select(nbr_select_kernel<kSelNE>));
   *row_redo_out = redo;
   *flags_out = flags;
+  *redo_list_out = reinterpret_cast<int*>(w + t.redo_list);
   return LANTERN_OK;
 }

@@ -140,6 +140,7 @@ __global__ void __launch_bounds__(NT + 64, (NT <= 256 ? 2 : 1)) row_stats_stream
   }
   __syncthreads();
 
+  const int rows_of_cta = (int)blockIdx.x < n_rows_total ? (n_rows_total - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
   if (tid >= NT) {
     // ================================================================================================== select warps
     const int sl = lane;
@@ -312,10 +313,7 @@ __global__ void __launch_bounds__(NT + 64, (NT <= 256 ? 2 : 1)) row_stats_stream
       if (sl == 0) mbar_arrive(&fs.mbar_done[hb]);
       ++jj;
     }
-    __syncthreads();   // publishes redo_n and the flagged records to the main threads
-    return;
-  }
-
+  } else {
   // ======================================================================================================= main threads
   uint32_t parity = 0, jj = 0;
   int item = (int)blockIdx.x / cfg.n_rows, trow = (int)blockIdx.x % cfg.n_rows;
@@ -490,8 +488,11 @@ __global__ void __launch_bounds__(NT + 64, (NT <= 256 ? 2 : 1)) row_stats_stream
     __syncwarp();
     if (lane == 0) mbar_arrive(&fs.mbar_ready[hb]);
   }
-  __syncthreads();   // pairs with the select warp's final barrier
-  if (fs.redo_n == 0) return;
+  }   // roles
+  __syncthreads();   // one barrier for both roles: publishes redo_n and the flagged records to the main threads
+  if (tid >= NT || fs.redo_n == 0) return;
+  uint32_t parity = (uint32_t)(rows_of_cta & 1);   // the TMA barrier has completed one phase per row of this CTA
+  int item, trow;
 
   // ---- redo: rows the streaming select could not finish; exact tiers 2 / 3 on the re-staged row ----
   item = (int)blockIdx.x / cfg.n_rows; trow = (int)blockIdx.x % cfg.n_rows;

@@ -33,6 +33,54 @@ def accept(params, phases=3):
         R.compare(res, i, o)
 
 
+def stream_rows():
+    from lantern_b200 import verify
+    rng = np.random.default_rng(3)
+    for ncols, dt, shape in ((2048, torch.float32, "gauss"), (4096, torch.bfloat16, "gauss"), (2048, torch.float32, "t2")):
+        B, T, top_k = 14, 59, 300                               # 826 rows on 296 CTAs
+        x = rng.standard_normal((B, T, ncols)) * 2.5 if shape == "gauss" else rng.standard_t(2, (B, T, ncols))
+        cond = torch.from_numpy(x.astype(np.float32)).cuda().to(dt)
+        uncond = torch.from_numpy((x + rng.standard_normal((B, T, ncols)) * 0.7).astype(np.float32)).cuda().to(dt)
+        fam = verify.LLAMAGEN.resized(ncols)
+        v = verify.Verifier(fam, temperature=1.0, top_k=top_k, cfg_scale=3.0, lantern=False, device=torch.device("cuda"))
+        tokens = torch.zeros(B, T, dtype=torch.int32, device="cuda")
+        retrieve = torch.zeros(B, 1, 1, dtype=torch.int32, device="cuda")
+        v.step(cond, uncond, tokens, retrieve, uniforms=torch.rand(B, 2, device="cuda"), phases=1)
+        torch.cuda.synchronize()
+        stats = v._work[:B * T * 32].view(torch.float32).view(B * T, 8).cpu().numpy()
+        s = O.cfg_mix(cond.float().cpu().numpy().reshape(-1, ncols), uncond.float().cpu().numpy().reshape(-1, ncols), 3.0)
+        kth = np.partition(s, ncols - top_k, axis=1)[:, ncols - top_k]
+        assert np.array_equal(stats[:, 0], kth) and np.array_equal(stats[:, 1], s.max(axis=1)), (ncols, dt, shape)
+
+
+def one_call():
+    import random
+    from lantern_b200 import synth, verify
+
+    class _M(PO.VerifyMixin):
+        lantern_family = "llamagen"
+        lantern_image_tokens = 2048
+    fam = O.small_family(O.LLAMAGEN, 2048)
+    tree = synth.eagle2_tree(5, 30, 4)
+    synth.assign_tokens(5, tree, 0, 2048)
+    cond, uncond = synth.tree_logits(5, tree, 2048, cfg=True, boost=11.0)
+    m = _M()
+    m.nearest_latents = synth.neighbor_table(0, 2048, 101)
+    ri = torch.from_numpy(tree.retrieve_indices).cuda()
+    toks = torch.from_numpy(tree.tokens).cuda()
+    cand = torch.cat([toks, torch.full((1,), -1, device="cuda", dtype=toks.dtype)])[ri]
+    handle = PO.TreeLogits(torch.from_numpy(cond).cuda()[None], torch.from_numpy(uncond).cuda()[None], 3.0, ri)
+    proc = PO.prepare_logits_processor(temperature=1.0, top_p=1.0, top_k=300)
+    random.seed(9)
+    st = random.getstate()
+    best, a, sp = m.evaluate_posterior(handle, cand, proc, lantern=True, lantern_k=100, lantern_delta=0.1)
+    random.setstate(st)
+    u = [random.random() for _ in range(tree.T)]
+    o = O.verify_step(cond, uncond, 3.0, tree.tokens, tree.retrieve_indices, np.asarray(u + [0.5]), fam,
+                      O.Warp(1.0, 1.0, 300), True, 100, 0.1, m.nearest_latents)
+    assert o.margin < 1e-5 or (int(best), a) == (o.best_candidate, o.accept_length)
+
+
 def main():
     torch.cuda.set_device(0)
     which = sys.argv[1:] or ["accept", "neighbors", "kv", "greedy", "drafter", "session"]
@@ -43,9 +91,14 @@ def main():
         accept(dict(family="anole", ncols=1024, top_k=0, top_p=0.9, lantern_k=50))                   # top-p kernel
         accept(dict(family="llamagen", ncols=2048, top_k=300, lantern_k=20, lantern_delta=5.0,
                     static_tree="mc_sim_7b_63", seed=500))                                           # static tree / LANTERN++
+        # round 2: streaming statistics kernel with several rows per CTA (select warps two rows behind), bf16 rows,
+        # non-Gaussian rows that miss the bracket (redo path), the 65536-column parity path, the one-call drop-in entry
+        stream_rows()
+        accept(dict(family="vanilla", ncols=65536, cfg=False, lantern=False, top_k=50, boost=13.0, total_tokens=8, seed=700))
+        one_call()
         print("accept ok", flush=True)
     if "neighbors" in which:
-        for N, d, K in ((1024, 8, 65), (512, 256, 33), (300, 8, 299)):
+        for N, d, K in ((1024, 8, 65), (512, 256, 33), (300, 8, 299), (2304, 8, 1001)):
             rng = np.random.default_rng(N + d)
             E = rng.standard_normal((N, d)).astype(np.float32)
             got = codebook.build_neighbor_table(torch.from_numpy(E).cuda(), K).cpu().numpy()

@@ -308,6 +308,35 @@ def test_row_statistics_exact_with_several_rows_per_cta(dist, ncols, top_k):
     _check_row_statistics(dist, ncols, top_k, B=40)
 
 
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_row_statistics_bitwise_reproducible(dtype):
+    """The streaming kernel hands rows from the main warps to the select warps through mbarriers (double-buffered);
+    whatever the timing, every launch must produce bit-identical records (threshold, maximum AND sum)."""
+    rng = np.random.default_rng(11)
+    B, T, ncols, top_k = 40, 33, 8192, 2000
+    x = rng.standard_normal((B, T, ncols)) * 2.5
+    x[:, ::7] = rng.standard_t(2, (B, len(range(0, T, 7)), ncols))          # some rows miss the bracket: redo path
+    cond = torch.from_numpy(x.astype(np.float32)).cuda().to(dtype)
+    uncond = torch.from_numpy((x + rng.standard_normal((B, T, ncols)) * 0.7).astype(np.float32)).cuda().to(dtype)
+    fam = verify.LLAMAGEN.resized(ncols)
+    v = verify.Verifier(fam, temperature=1.0, top_k=top_k, cfg_scale=3.0, lantern=False, device=torch.device("cuda"))
+    tokens = torch.zeros(B, T, dtype=torch.int32, device="cuda")
+    retrieve = torch.zeros(B, 1, 1, dtype=torch.int32, device="cuda")
+    uni = torch.rand(B, 2, device="cuda")
+    first = None
+    junk = torch.empty(64 << 20, dtype=torch.uint8, device="cuda")
+    for rep in range(6):
+        if rep % 2:
+            junk.random_(0, 255)                     # perturb cache state / timing between launches
+        v.step(cond, uncond, tokens, retrieve, uniforms=uni, phases=1)
+        torch.cuda.synchronize()
+        stats = v._work[:B * T * 32].view(torch.int32).view(B * T, 8)[:, :3].clone()
+        if first is None:
+            first = stats
+        else:
+            assert torch.equal(stats, first), f"launch {rep}: {int((stats != first).any(1).sum())} rows differ"
+
+
 def _check_row_statistics(dist, ncols, top_k, B):
     rng = np.random.default_rng(hash((dist, ncols)) % 2**32)
     T = 33

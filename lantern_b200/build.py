@@ -41,16 +41,22 @@ def needs_build() -> bool:
     return any(os.path.getmtime(d) > t for d in _deps())
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    if not force and not needs_build():
+def build(force: bool = False, verbose: bool = False, variant: str = "", flags: List[str] = ()) -> str:
+    """``variant``: an A/B or profiling build next to the product library (``lantern_b200/variants/lib_<variant>.so``,
+    extra nvcc ``flags``); select it at run time with LANTERN_B200_LIB."""
+    lib = LIB
+    if variant:
+        os.makedirs(os.path.join(PKG, "variants"), exist_ok=True)
+        lib = os.path.join(PKG, "variants", f"lib_{variant}.so")
+    elif not force and not needs_build():
         return LIB
     nvcc = _nvcc()
     objs = []
     log = []
-    objdir = os.path.join(PKG, "build")
+    objdir = os.path.join(PKG, "build" + ("_" + variant if variant else ""))
     os.makedirs(objdir, exist_ok=True)
     procs = []
-    extra = os.environ.get("LANTERN_EXTRA_NVCC_FLAGS", "").split()
+    extra = os.environ.get("LANTERN_EXTRA_NVCC_FLAGS", "").split() + list(flags)
     for src in SOURCES:
         obj = os.path.join(objdir, src.replace(".cu", ".o"))
         cmd = [nvcc] + NVCC_FLAGS + extra + ["-I", os.path.join(ROOT, "include"), "-c", os.path.join(CSRC, src), "-o", obj]
@@ -61,7 +67,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         log.append(f"$ {' '.join(cmd)}\n{out}")
         if p.returncode != 0:
             raise RuntimeError(f"nvcc failed on {src}:\n{out}")
-    link = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + objs
+    link = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", lib] + objs
     r = subprocess.run(link, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     log.append(f"$ {' '.join(link)}\n{r.stdout}")
     if r.returncode != 0:
@@ -70,8 +76,12 @@ def build(force: bool = False, verbose: bool = False) -> str:
         f.write("\n".join(log))
     if verbose:
         print("\n".join(log))
-    return LIB
+    return lib
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    if "--variant" in sys.argv:   # python -m lantern_b200.build --variant trace -DLANTERN_WALK_TRACE
+        i = sys.argv.index("--variant")
+        print(build(variant=sys.argv[i + 1], flags=sys.argv[i + 2:]))
+    else:
+        print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

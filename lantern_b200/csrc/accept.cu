@@ -30,8 +30,26 @@
 
 namespace lantern {
 
+// Phase trace of the walk (profiling builds only: -DLANTERN_WALK_TRACE, profiles/walk_trace.py).  Thread 0 of every CTA
+// keeps (tag, clock) pairs in shared memory and copies them out once at the end, so a mark costs a few cycles.
+#ifdef LANTERN_WALK_TRACE
+constexpr int kTraceMax = 120, kTraceBlocks = 256;
+__device__ long long g_trace[kTraceBlocks][2 * kTraceMax + 2];
+__shared__ long long tr_buf[2 * kTraceMax];
+__shared__ int tr_n;
+#define TR(tag) do { if (threadIdx.x == 0 && tr_n < kTraceMax) { tr_buf[2 * tr_n] = (tag); tr_buf[2 * tr_n + 1] = clock64(); ++tr_n; } } while (0)
+#else
+#define TR(tag) do { } while (0)
+#endif
+
 constexpr int kWalkThreads = 1024;
-constexpr int kLazyThreads = 512;   // lazy schedule: fewer, fatter threads (16 row values each at 8192 columns) and cheaper barriers
+// Lazy schedule: few, fat threads (32 row values each at 8192 columns).  The walk CTA is alone on its SM and most of its
+// instructions are per-thread bookkeeping every warp repeats (reduction tails, scans, address arithmetic): with W warps
+// on four schedulers each such instruction costs W/4 issue cycles, so 8 warps beat 16 (and 16 beat 32, round 1).
+#ifndef LANTERN_LAZY_THREADS
+#define LANTERN_LAZY_THREADS 256
+#endif
+constexpr int kLazyThreads = LANTERN_LAZY_THREADS;
 constexpr int kMaxSib = 64;
 
 
@@ -194,6 +212,10 @@ struct WalkSmem {
   float* uni;        // [T + 1] this item's uniforms (supplied or Philox)
   int* sib;          // [kMaxSib] tokens of the rejected node's earlier siblings
   int* pid;          // [L] rows still matching the accepted prefix
+  int* ctok;         // [L*D] token at every (row, level) of the path table, -1 = padding
+  int* csyn;         // [L*D] Lumina: the token at (row, level) is a syntax token (accepted with p = 1)
+  int* maxcp;        // [L] longest token prefix a row shares with an earlier row (static: dedup of the children)
+  int* kid_syn;      // [L] Lumina: the child token is a syntax token (accepted with p = 1)
   double* dscr;      // [34]
   float* fscr;       // [34]
   int* iscr;         // [40]
@@ -267,85 +289,296 @@ __device__ __forceinline__ RowStats raw_row_stats(const AcceptParams& P, int b, 
 // Lazy mode (phases bit 2): statistics of a visited row computed inside the walk CTA, straight from the logits,
 // and the probability vector written from registers (one global read of the row instead of two, and no
 // statistics for the ~85 % of tree rows the walk never visits).  Same arithmetic as the streamed kernels.
-// Returns true (and writes nothing) when every live column is -inf: a pre-masked one-hot row (see set_distribution).
-template <int DT, int NE>
+//
+// The walk waits for every row it visits, so this routine is built for latency, not throughput (round 2: the first
+// version spent 13 block barriers and two MUFU passes per row, ~7800 cycles after the loads had landed):
+//   * four barriers on the common path: moments, bracket counts + histogram, candidate list, kept mass;
+//   * exp() once per element (the kept-mass sum and the probability vector use the same register copy);
+//   * everything a single warp used to do behind a barrier (histogram scan, exact ranking of the handful of
+//     candidates) is done by every warp redundantly from the same shared-memory data - no broadcast barrier;
+//   * `hook` runs between issuing the row's loads and their first use: the walk lists the children of the current node
+//     (one warp) inside the load shadow; `post` runs behind the first barrier, where the hook's results are visible.
+// Rows the moment bracket misses (non-Gaussian rows, heavy ties, non-finite values) take the exact tier-2/3 selectors
+// of select.cuh as before.  Returns true (and writes nothing) when every live column is -inf: a pre-masked one-hot
+// row (see set_distribution).
+constexpr int kLazyListMax = 128;
+struct LazySmem {
+  float4 mom[kLazyThreads / 32];        // per-warp (sum, sum of squares, min, max)
+  int4 cnt[kLazyThreads / 32];          // per-warp (elements above the bracket, parked elements, bits of their exp-sum, -)
+  unsigned wh[kLazyThreads / 32][8];    // per-warp counts of the 16 bracket fields, two 16-bit counts per word
+  float part[kLazyThreads / 32];        // per-warp kept mass
+  float thr;
+  float list[kLazyListMax];
+};
+
+template <int DT, int NE, class Hook, class Post>
 __device__ __forceinline__ bool lazy_probs(const AcceptParams& P, int b, int node, bool raw, float* p, float* park,
-                                           SelectSmem& sm, float* part_scr, float& z_run, float& win_run) {
+                                           LazySmem& lz, SelectSmem& sm, float& z_run, float& win_run, Hook&& hook,
+                                           Post&& post) {
   constexpr int NT = kLazyThreads, NW = NT / 32, NQ = NE / 4;
+  constexpr unsigned kFull = 0xffffffffu;
+  static_assert(NW % 4 == 0 && NW <= 32, "the field totals below are gathered by 4 lane groups x NW/4 warps");
   const lantern_accept_cfg& cfg = P.cfg;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int64_t base = (int64_t)b * cfg.item_stride + (int64_t)node * cfg.row_stride + cfg.col0;
   MixParams mix = P.mix;
   if (raw) mix.do_temp = 0;
-  float s[NE];
-  float fsum = 0.f, fsq = 0.f, fmn = INFINITY, fmx = -INFINITY;
+  // ---- the row's loads go out first; nothing below touches them until the hook has run ----
+  float cc[NQ][4], uu[NQ][4];
 #pragma unroll
   for (int q = 0; q < NQ; ++q) {
     const int e0 = (q * NT + tid) * 4;
-    float c4[4], u4[4] = {0.f, 0.f, 0.f, 0.f};
-    Elem<DT>::load4(P.in.logits_cond, base + e0, c4);
-    if (mix.has_uncond) Elem<DT>::load4(P.in.logits_uncond, base + e0, u4);
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const float v = mix_temper(c4[j], u4[j], mix);
-      s[q * 4 + j] = v;
-      fsum += v; fsq = fmaf(v, v, fsq); fmn = fminf(fmn, v); fmx = fmaxf(fmx, v);
-    }
+    Elem<DT>::load4(P.in.logits_cond, base + e0, cc[q]);
+    if (mix.has_uncond) Elem<DT>::load4(P.in.logits_uncond, base + e0, uu[q]);
+    else { uu[q][0] = uu[q][1] = uu[q][2] = uu[q][3] = 0.f; }
   }
-  fsum = warp_reduce(fsum, OpSum()); fsq = warp_reduce(fsq, OpSum());
-  fmn = -warp_reduce(-fmn, OpMaxF()); fmx = warp_reduce(fmx, OpMaxF());
-  __syncthreads();
-  if (lane == 0) { sm.f4[0][warp] = fsum; sm.f4[1][warp] = fsq; sm.f4[2][warp] = fmn; sm.f4[3][warp] = fmx; }
-  __syncthreads();
-  fsum = 0.f; fsq = 0.f; fmn = INFINITY; fmx = -INFINITY;
-#pragma unroll 8
+  hook();
+  TR(39);
+  // The SM handles 128 lanes per clock, so every instruction spent per element costs 64 cycles of an 8192-column row:
+  // the passes below are written for instruction count (packed fp32 pairs, predicated adds, a running store pointer).
+  float s[NE];
+  float fsum, fsq, fmx = -INFINITY;
+  {
+    uint64_t sum2 = pack2(0.f, 0.f), sq2 = pack2(0.f, 0.f);
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) {
+#pragma unroll
+      for (int j = 0; j < 4; j += 2) {
+        const uint64_t v2 = mix_temper2(cc[q][j], cc[q][j + 1], uu[q][j], uu[q][j + 1], mix);
+        unpack2(v2, s[q * 4 + j], s[q * 4 + j + 1]);
+        sum2 = add2(sum2, v2);
+        sq2 = fma2(v2, v2, sq2);
+        fmx = fmaxf(fmx, fmaxf(s[q * 4 + j], s[q * 4 + j + 1]));
+      }
+    }
+    float a0, a1;
+    unpack2(sum2, a0, a1); fsum = a0 + a1;
+    unpack2(sq2, a0, a1); fsq = a0 + a1;
+  }
+  TR(40);
+  {
+    // the maximum through integer keys (one REDUX); the two sums share one butterfly: after the first exchange the lower
+    // half-warp carries the sum, the upper one the sum of squares
+    const unsigned kmx = __reduce_max_sync(kFull, float_key(fmx));
+    const bool up = (lane & 16) != 0;
+    float keep = up ? fsq : fsum;
+    keep += __shfl_xor_sync(kFull, up ? fsum : fsq, 16);
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) keep += __shfl_xor_sync(kFull, keep, o);
+    if (lane == 0) { lz.mom[warp].x = keep; lz.mom[warp].w = key_float(kmx); }
+    if (lane == 16) lz.mom[warp].y = keep;
+  }
+  __syncthreads();   // #1 (also publishes what the hook wrote)
+  post();
+  fsum = 0.f; fsq = 0.f; fmx = -INFINITY;
+#pragma unroll
   for (int w = 0; w < NW; ++w) {
-    fsum += sm.f4[0][w]; fsq += sm.f4[1][w]; fmn = fminf(fmn, sm.f4[2][w]); fmx = fmaxf(fmx, sm.f4[3][w]);
+    const float4 m = lz.mom[w];
+    fsum += m.x; fsq += m.y; fmx = fmaxf(fmx, m.w);
   }
   if (fmx == -INFINITY) return true;   // block-uniform
-  float thr = -INFINITY;
+  TR(41);
+  const ExpShift ex(fmx);
+  float ev[NE];
+  float thr = -INFINITY, tot = 0.f;
+  bool have_tot = false;
   if (P.do_topk && !raw) {
-    bool found = false;
-    const bool finite = isfinite(fmn) && isfinite(fmx) && isfinite(fsq);
+    // a finite sum of squares means every element is finite (a constant row ends on the slow path: its bracket is
+    // empty or holds the whole row)
+    const bool finite = isfinite(fmx) && isfinite(fsq);
     const float inv_n = 1.0f / (float)cfg.ncols;
     const float mean = fsum * inv_n;
     const float sd = sqrtf(fmaxf(fsq * inv_n - mean * mean, 0.f));
-    if (finite && fmn == fmx) { thr = fmx; found = true; }
-    if (!found && finite) {
+    const int k = cfg.top_k;
+    bool slow = false;
+    {
       const float lo = mean + (z_run - win_run) * sd, hi = mean + (z_run + win_run) * sd;
-      if (lo < hi) found = bracket_select<NE, NT>(s, cfg.top_k, lo, hi, park, sm, &thr);
+      const Classifier cls = make_classifier(lo, hi);   // 16 fields; the bracket itself is tiled by fields 1..14
+      const bool fast = finite && lo < hi && isfinite(cls.scale) && isfinite(cls.bias23);
+      // One sweep: exp of every element, count and exp-sum of the elements above the bracket, the elements inside it
+      // parked in the thread's private shared-memory column (branch-free: every element is stored at the running slot,
+      // only an element inside the bracket keeps it).  No shared-memory atomics anywhere in this routine: they cost
+      // two cycles per lane on this machine, which made a 64-field atomic histogram the most expensive step of the row.
+      int above = 0, slot = 0;
+      float sum_ab = 0.f;
+      if (fast) {
+        float* pp = park + tid;
+#pragma unroll
+        for (int e = 0; e < NE; ++e) {
+          const float v = s[e];
+          const float x = ex(v);
+          ev[e] = x;
+          const bool ab = v > hi;
+          if (ab) { sum_ab += x; ++above; }
+          *pp = v;
+          if (!ab && v >= lo) pp += NT;
+        }
+        slot = (int)(pp - (park + tid)) / NT;
+      } else {
+#pragma unroll
+        for (int e = 0; e < NE; ++e) ev[e] = ex(s[e]);
+      }
+      slow = !fast;
+      if (fast) {
+        // the thread's parked elements by field: sixteen 8-bit counters in two registers (a thread parks <= NE <= 32)
+        unsigned long long ca = 0ull, cb = 0ull;
+        for (int i = 0; i < slot; ++i) {
+          const unsigned f = cls(park[i * NT + tid]);
+          const unsigned long long inc = 1ull << ((f & 7u) * 8u);
+          if (f < 8u) ca += inc; else cb += inc;
+        }
+        // widen to 16-bit pairs and add across the warp: word 2q + r holds fields 4q + r and 4q + r + 2 (r = 0, 1)
+        unsigned wsum[8];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const unsigned w32 = q < 2 ? (unsigned)(ca >> (32 * q)) : (unsigned)(cb >> (32 * (q - 2)));
+          wsum[2 * q] = __reduce_add_sync(kFull, w32 & 0x00ff00ffu);
+          wsum[2 * q + 1] = __reduce_add_sync(kFull, (w32 >> 8) & 0x00ff00ffu);
+        }
+        const int w_above = __reduce_add_sync(kFull, above), w_in = __reduce_add_sync(kFull, slot);
+        const int max_slot = __reduce_max_sync(kFull, slot);
+        sum_ab = warp_reduce(sum_ab, OpSum());
+        if (lane == 0) {
+          lz.cnt[warp] = make_int4(w_above, w_in, __float_as_int(sum_ab), 0);
+          *reinterpret_cast<uint4*>(&lz.wh[warp][0]) = make_uint4(wsum[0], wsum[1], wsum[2], wsum[3]);
+          *reinterpret_cast<uint4*>(&lz.wh[warp][4]) = make_uint4(wsum[4], wsum[5], wsum[6], wsum[7]);
+        }
+        TR(45);
+        __syncthreads();   // #2
+        int tot_above = 0, tot_in = 0;
+        float sum_above = 0.f;
+#pragma unroll
+        for (int w = 0; w < NW; ++w) {
+          const int4 c = lz.cnt[w];
+          tot_above += c.x; tot_in += c.y; sum_above += __int_as_float(c.z);
+        }
+        TR(46);
+        if (tot_above < k && k <= tot_above + tot_in) {
+          const int krem = k - tot_above;   // rank among the parked elements
+          // Every warp finds the field F that holds the target itself.  Block totals of the packed words (they still
+          // fit 16 bits: at most 16384 elements): lane l adds word l & 7 of NW/4 warps, two exchanges finish the sum.
+          unsigned wt = 0u;
+          {
+            const int t = lane & 7, g = lane >> 3;
+#pragma unroll
+            for (int i = 0; i < NW / 4; ++i) wt += lz.wh[g * (NW / 4) + i][t];
+            wt += __shfl_xor_sync(kFull, wt, 8);
+            wt += __shfl_xor_sync(kFull, wt, 16);
+          }
+          // lane f (and its mirror f + 16) takes field f: word 2 (f >> 2) + (f & 1), upper half when f & 2
+          const int f = lane & 15;
+          const unsigned wf = __shfl_sync(kFull, wt, 2 * (f >> 2) + (f & 1));
+          const unsigned cf = (f & 2) ? (wf >> 16) : (wf & 0xffffu);
+          unsigned incl = cf;   // suffix sums from the top field down
+#pragma unroll
+          for (int o = 1; o < 16; o <<= 1) {
+            const unsigned n = __shfl_down_sync(kFull, incl, o, 16);
+            if (f + o < 16) incl += n;
+          }
+          const unsigned above_f = incl - cf;
+          const bool mine = above_f < (unsigned)krem && above_f + cf >= (unsigned)krem;
+          const unsigned owner_mask = __ballot_sync(kFull, mine) & 0xffffu;
+          const int F = owner_mask ? __ffs(owner_mask) - 1 : -1;
+          const int above2 = (int)__shfl_sync(kFull, above_f, F >= 0 ? F : 0);
+          const int cntF = (int)__shfl_sync(kFull, cf, F >= 0 ? F : 0);
+          TR(47);
+          if (F >= 0 && cntF <= kLazyListMax) {
+            // the members of F go into one list, in (warp, slot, lane) order - a fixed order, so every sum over the
+            // list is reproducible; the warp's offset comes from the per-warp field counts, no atomics
+            int pos;
+            {
+              const unsigned ww = lane < NW ? lz.wh[lane][2 * (F >> 2) + (F & 1)] : 0u;
+              const unsigned cw = (F & 2) ? (ww >> 16) : (ww & 0xffffu);
+              pos = (int)__reduce_add_sync(kFull, lane < warp ? cw : 0u);
+            }
+            float part = 0.f;   // kept mass of the thread's parked elements in fields above F (they are above thr)
+            for (int i = 0; i < max_slot; ++i) {
+              const bool have = i < slot;
+              const float v = have ? park[i * NT + tid] : 0.f;
+              const unsigned fv = have ? cls(v) : 0xffffu;
+              const unsigned m = __ballot_sync(kFull, fv == (unsigned)F);
+              if (fv == (unsigned)F) lz.list[pos + __popc(m & ((1u << lane) - 1u))] = v;
+              pos += __popc(m);
+              if (have && fv > (unsigned)F) part += ex(v);
+            }
+            part = warp_reduce(part, OpSum());
+            if (lane == 0) lz.part[warp] = part;
+            __syncthreads();   // #3
+            TR(48);
+            // exact rank inside field F: one candidate per thread against the whole list
+            const int kr = krem - above2;
+            for (int i = tid; i < cntF; i += NT) {   // one candidate per lane: only the first cntF / 32 warps work
+              const float vi = lz.list[i];
+              int gt = 0, ge = 0;
+#pragma unroll 4
+              for (int j = 0; j < cntF; ++j) {
+                const float vj = lz.list[j];   // broadcast read
+                gt += vj > vi;
+                ge += vj >= vi;
+              }
+              if (gt < kr && kr <= ge) lz.thr = vi;   // every qualifying candidate has the same value
+            }
+            __syncthreads();   // #4
+            thr = lz.thr;
+            TR(49);
+            float fm = 0.f;   // kept mass inside F, the same fixed order in every warp
+            for (int i = lane; i < cntF; i += 32) {
+              const float vi = lz.list[i];
+              fm += vi >= thr ? ex(vi) : 0.f;
+            }
+            fm = warp_reduce(fm, OpSum());
+            tot = sum_above;
+#pragma unroll
+            for (int w = 0; w < NW; ++w) tot += lz.part[w];
+            tot += fm;
+            have_tot = true;
+          } else {
+            slow = true;
+          }
+        } else {
+          slow = true;
+        }
+      }
     }
-    if (!found) {
+    TR(42);
+    if (slow) {   // block-uniform
       __syncthreads();
       float tmp[NE];
+      float fmn = INFINITY;   // the fast path has no use for the row minimum
 #pragma unroll
-      for (int e = 0; e < NE; ++e) tmp[e] = s[e];
-      thr = select_slow<NE>(tmp, cfg.top_k, fmn, fmx, sm);
+      for (int e = 0; e < NE; ++e) { tmp[e] = s[e]; fmn = fminf(fmn, s[e]); }
+      fmn = -block_reduce(-fmn, OpMaxF(), -INFINITY, sm.f4[0]);
+      thr = select_slow<NE>(tmp, k, fmn, fmx, sm);
       __syncthreads();
     }
     const float z_obs = (thr - mean) / sd;
     if (isfinite(z_obs)) { z_run = z_obs; win_run = P.win_sd; }   // a walk visits too few rows to adapt the width
-  }
-  const ExpShift ex(fmx);
-  float part = 0.f;
+  } else {
 #pragma unroll
-  for (int e = 0; e < NE; ++e) part += (s[e] >= thr) ? ex(s[e]) : 0.f;
-  part = warp_reduce(part, OpSum());
-  __syncthreads();
-  if (lane == 0) part_scr[warp] = part;
-  __syncthreads();
-  float tot = 0.f;
-#pragma unroll 8
-  for (int w = 0; w < NW; ++w) tot += part_scr[w];
+    for (int e = 0; e < NE; ++e) ev[e] = ex(s[e]);
+  }
+  if (!have_tot) {
+    float part = 0.f;
+#pragma unroll
+    for (int e = 0; e < NE; ++e) part += (s[e] >= thr) ? ev[e] : 0.f;
+    part = warp_reduce(part, OpSum());
+    __syncthreads();
+    if (lane == 0) lz.part[warp] = part;
+    __syncthreads();
+    tot = 0.f;
+#pragma unroll
+    for (int w = 0; w < NW; ++w) tot += lz.part[w];
+  }
   const float inv = __fdiv_rn(1.0f, tot);
+  TR(44);
 #pragma unroll
   for (int q = 0; q < NQ; ++q) {
     const int e0 = (q * NT + tid) * 4;
     float4 o;
-    o.x = s[q * 4 + 0] >= thr ? __fmul_rn(ex(s[q * 4 + 0]), inv) : 0.f;
-    o.y = s[q * 4 + 1] >= thr ? __fmul_rn(ex(s[q * 4 + 1]), inv) : 0.f;
-    o.z = s[q * 4 + 2] >= thr ? __fmul_rn(ex(s[q * 4 + 2]), inv) : 0.f;
-    o.w = s[q * 4 + 3] >= thr ? __fmul_rn(ex(s[q * 4 + 3]), inv) : 0.f;
+    o.x = s[q * 4 + 0] >= thr ? __fmul_rn(ev[q * 4 + 0], inv) : 0.f;
+    o.y = s[q * 4 + 1] >= thr ? __fmul_rn(ev[q * 4 + 1], inv) : 0.f;
+    o.z = s[q * 4 + 2] >= thr ? __fmul_rn(ev[q * 4 + 2], inv) : 0.f;
+    o.w = s[q * 4 + 3] >= thr ? __fmul_rn(ev[q * 4 + 3], inv) : 0.f;
     *reinterpret_cast<float4*>(p + e0) = o;
   }
   return false;
@@ -384,37 +617,73 @@ __global__ void __launch_bounds__(LNE > 0 ? kLazyThreads : kWalkThreads) walk_ke
   S.fscr = reinterpret_cast<float*>(smem_raw + o);          o += 36 * 4;
   S.iscr = reinterpret_cast<int*>(smem_raw + o);            o += 40 * 4;
   S.pid = reinterpret_cast<int*>(smem_raw + o);                 o += (size_t)((L + 3) & ~3) * 4;
+  S.maxcp = reinterpret_cast<int*>(smem_raw + o);               o += (size_t)((L + 3) & ~3) * 4;
+  S.ctok = reinterpret_cast<int*>(smem_raw + o);                o += (size_t)((L * D + 3) & ~3) * 4;
+  S.csyn = reinterpret_cast<int*>(smem_raw + o);                o += (size_t)((L * D + 3) & ~3) * 4;
+  S.kid_syn = reinterpret_cast<int*>(smem_raw + o);             o += (size_t)((L + 3) & ~3) * 4;
   o = (o + 7) & ~size_t(7);
   double* rsum = reinterpret_cast<double*>(smem_raw + o);       o += 2 * 32 * 8;   // removed-mass partials, two parities
   float* lazy_park = reinterpret_cast<float*>(smem_raw + o);   // [LNE][kLazyThreads] (lazy modes only)
   __shared__ SelectSmem lazy_sm;
-  __shared__ float lazy_part[32];
+  __shared__ LazySmem lazy_lz;
   float z_run = P.z_guess, win_run = P.win_sd_first;
 
+#ifdef LANTERN_WALK_TRACE
+  if (threadIdx.x == 0) tr_n = 0;
+#endif
+  TR(1);
   const int* ri_g = P.in.retrieve + (cfg.retrieve_shared ? 0 : (size_t)b * L * D);
   const int* tok_g = P.in.tree_tokens + (size_t)b * T;
-  for (int i = tid; i < L * D; i += NT) S.ri[i] = ri_g[i];
-  for (int i = tid; i < T; i += NT) S.tok[i] = tok_g[i];
-  // at most one draw per tree node plus the bonus token (SURVEY.md Appendix A "uniform budget")
-  for (int i = tid; i < T + 1; i += NT) {
-    float uv;
-    if (P.in.uniforms) uv = i < cfg.n_uniforms ? P.in.uniforms[(size_t)b * cfg.n_uniforms + i] : 0.f;
-    else uv = philox_uniform(cfg.philox_seed, cfg.philox_step, (uint32_t)b, (uint32_t)i);
-    S.uni[i] = uv;
-  }
-  WB::sync();
-  auto cand = [&](int j, int i) -> int {
-    const int n = S.ri[j * D + i];
-    return n >= 0 ? S.tok[n] : -1;
-  };
+  auto cand = [&](int j, int i) -> int { return S.ctok[j * D + i]; };   // token of row j at level i, -1 = padding
   // Rows still matching the accepted prefix (the reference's `is_eq`, ea_model_llamagen.py:721): every row that starts
   // with row 0's root token; an acceptance at level i keeps the rows whose token at level i is the accepted one.
   int* member = S.pid;   // [L]
-  {
-    const int root_tok = cand(0, 0);
-    for (int j = tid; j < L; j += NT) member[j] = cand(j, 0) == root_tok ? 1 : 0;
-  }
-  WB::sync();
+  // Staging of the prompt's tree.  In the lazy form it runs inside the load shadow of the root's logits row (as part of
+  // the first level's hook, see the level loop): the walk is a latency chain and this is ~1.5 us of it.
+  auto prologue = [&]() {
+    for (int i = tid; i < L * D; i += NT) S.ri[i] = ri_g[i];
+    for (int i = tid; i < T; i += NT) S.tok[i] = tok_g[i];
+    // at most one draw per tree node plus the bonus token (SURVEY.md Appendix A "uniform budget")
+    for (int i = tid; i < T + 1; i += NT) {
+      float uv;
+      if (P.in.uniforms) uv = i < cfg.n_uniforms ? P.in.uniforms[(size_t)b * cfg.n_uniforms + i] : 0.f;
+      else uv = philox_uniform(cfg.philox_seed, cfg.philox_step, (uint32_t)b, (uint32_t)i);
+      S.uni[i] = uv;
+    }
+    WB::sync();
+    for (int i = tid; i < L * D; i += NT) {
+      const int n = S.ri[i];
+      const int x = n >= 0 ? S.tok[n] : -1;
+      S.ctok[i] = x;
+      int syn = 0;
+      if (P.lumina)
+        for (int q = 0; q < cfg.n_syntax; ++q) syn |= (cfg.syntax_tokens[q] == x) ? 1 : 0;
+      S.csyn[i] = syn;
+    }
+    WB::sync();
+    {
+      const int root_tok = cand(0, 0);
+      for (int j = tid; j < L; j += NT) member[j] = cand(j, 0) == root_tok ? 1 : 0;
+    }
+    // The reference lists the distinct child tokens of the current node in row order (`candidates_set`,
+    // ea_model_llamagen.py:728-739).  The rows in play at level l all carry the accepted tokens at levels < l, so row
+    // j repeats an earlier row's token at level l exactly when an earlier row shares j's token prefix through level l:
+    // a property of the tree alone.  maxcp[j] = the longest token prefix row j shares with any earlier row.
+    for (int j = tid >> 5; j < L; j += NT >> 5) {
+      int longest = 0;
+      for (int jj = tid & 31; jj < j; jj += 32) {
+        int cp = D;
+        for (int l = D - 1; l >= 0; --l)
+          if (S.ctok[jj * D + l] != S.ctok[j * D + l]) cp = l;
+        longest = max(longest, cp);
+      }
+      longest = __reduce_max_sync(0xffffffffu, longest);
+      if ((tid & 31) == 0) S.maxcp[j] = longest;
+    }
+    WB::sync();
+  };
+  const bool defer_prologue = LNE > 0 && D > 1;
+  if (!defer_prologue) prologue();
 
   // ---- distribution state: window S.p + one explicit out-of-window token + uniform remainder ----
   // The residual is stored unnormalised: probability = stored value * scale.  A rejection then only zeroes
@@ -444,15 +713,19 @@ __global__ void __launch_bounds__(LNE > 0 ? kLazyThreads : kWalkThreads) walk_ke
   double win_tot = 0.0;
   bool win_tot_valid = false;
   unsigned rej_parity = 0;
-  auto set_distribution = [&](int node, bool raw) {
+  // `hook` (lazy form only): work for one warp that does not depend on the row - it runs while the row's loads are in
+  // flight and is published by the barriers below
+  auto set_distribution = [&](int node, bool raw, auto&& hook, auto&& post) {
     const long long row = (long long)b * T + node;
     RowStats st;
     if (LNE > 0) {   // lazy mode: only the row class is needed up front
       st.kind = P.in.row_kinds ? (int)P.in.row_kinds[row] : LANTERN_ROW_IMAGE;
+      // no barrier here: S.p is rewritten only behind the barriers of lazy_probs, which every earlier reader has passed
+      if (st.kind != LANTERN_ROW_IMAGE) { hook(); WB::sync(); post(); }
     } else {
       st = P.stats[row];
+      WB::sync();
     }
-    WB::sync();
     extra_tok = -1; p_extra = 0.f; p_out = 0.f; scale = 1.0f;
     dist_node = node; dist_dirty = false; dist_raw = raw;
     win_tot_valid = false;
@@ -461,7 +734,7 @@ __global__ void __launch_bounds__(LNE > 0 ? kLazyThreads : kWalkThreads) walk_ke
       bool empty;
       if (LNE > 0) {
         ++rows_read;
-        empty = lazy_probs<DT, (LNE > 0 ? LNE : 4)>(P, b, node, raw, S.p, lazy_park, lazy_sm, lazy_part, z_run, win_run);
+        empty = lazy_probs<DT, (LNE > 0 ? LNE : 8)>(P, b, node, raw, S.p, lazy_park, lazy_lz, lazy_sm, z_run, win_run, hook, post);
       } else {
         ++rows_read;
         if (raw) st = raw_row_stats<DT, VEC>(P, b, node, S.fscr, S.dscr);
@@ -493,86 +766,113 @@ __global__ void __launch_bounds__(LNE > 0 ? kLazyThreads : kWalkThreads) walk_ke
     WB::sync();
   };
   auto uniform = [&](int d) -> float { return S.uni[min(d, T)]; };
-  auto is_syntax = [&](int tkn) -> bool {
-    for (int i = 0; i < cfg.n_syntax; ++i)
-      if (cfg.syntax_tokens[i] == tkn) return true;
-    return false;
+  // speculative L2 prefetch of a child's logits row (a wasted prefetch costs 64 KiB of otherwise idle HBM bandwidth)
+  auto prefetch_row = [&](int cnode, int lvl) {
+    if (!P.prefetch_rows || cnode < 0 || lvl + 1 >= D) return;
+    constexpr size_t eb = Elem<DT>::kBytes;
+    const int64_t nbase = (int64_t)b * cfg.item_stride + (int64_t)cnode * cfg.row_stride + col0;
+    const uintptr_t a0 = (reinterpret_cast<uintptr_t>(P.in.logits_cond) + nbase * eb + 15) & ~uintptr_t(15);
+    const uintptr_t a1 = (reinterpret_cast<uintptr_t>(P.in.logits_cond) + (nbase + ncols) * eb) & ~uintptr_t(15);
+    if (a1 > a0) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a0), "r"((unsigned)(a1 - a0)));
+    if (P.mix.has_uncond) {
+      const uintptr_t b0 = (reinterpret_cast<uintptr_t>(P.in.logits_uncond) + nbase * eb + 15) & ~uintptr_t(15);
+      const uintptr_t b1 = (reinterpret_cast<uintptr_t>(P.in.logits_uncond) + (nbase + ncols) * eb) & ~uintptr_t(15);
+      if (b1 > b0) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(b0), "r"((unsigned)(b1 - b0)));
+    }
   };
-
   int accept_length = 1, best = 0, draws = 0, out_flags = 0;
   bool adjust = false;
   const int kk = cfg.lantern ? min(cfg.lantern_k, cfg.table_cols) : 0;
   const int kk1 = cfg.lantern ? min(cfg.lantern_k + 1, cfg.table_cols) : 0;
 
+  TR(2);
   for (int lvl = 1; lvl < D; ++lvl) {
     if (lvl != accept_length) break;
     adjust = false;
+    TR(10 + lvl);
+    // fi, the first row still matching the accepted prefix (`member` was last written behind a barrier): every warp
+    // finds it for itself
+    const bool staging = defer_prologue && lvl == 1;   // the tree is not in shared memory yet: row 0 is always in play
+    int fi = 0;
+    for (int jb = 0; jb < L && !staging; jb += 32) {
+      const int j = jb + (tid & 31);
+      const unsigned mm = __ballot_sync(0xffffffffu, j < L && member[j] != 0);
+      if (mm) { fi = jb + __ffs(mm) - 1; break; }
+    }
+    int node = staging ? __ldg(ri_g) : S.ri[fi * D + lvl - 1];
+    if (node < 0) node += T;
+    TR(35);
     // Warp 0 lists the distinct children of the current node in row order (the reference's `candidates_set`
-    // dedup, ea_model_llamagen.py:728-739) and finds fi, the first row still matching the accepted prefix.
-    if (tid < 32) {
-      int n = 0, first_member = -1;
+    // dedup, ea_model_llamagen.py:728-739).  In the lazy form this runs while the node's logits row is in flight.
+    auto list_children = [&]() {
+      if (tid >= 32) return;
+      int n = 0;
+#pragma unroll 2
       for (int jb = 0; jb < L; jb += 32) {
         const int j = jb + tid;
         const bool mem = j < L && member[j] != 0;
-        const unsigned mm = __ballot_sync(0xffffffffu, mem);
-        if (first_member < 0 && mm) first_member = jb + __ffs(mm) - 1;
         int x = -1, cn = -1;
         if (mem) {
           cn = S.ri[j * D + lvl];
-          x = cn >= 0 ? S.tok[cn] : -1;
+          x = S.ctok[j * D + lvl];
         }
-        // first occurrence of the token: lowest lane of its match group in this chunk, and not listed by an earlier chunk
-        const unsigned peers = __match_any_sync(0xffffffffu, x != -1 ? x : -2 - tid);
-        bool first = x != -1 && tid == __ffs(peers) - 1;
-        for (int q = 0; q < n; ++q) first = first && (S.tried[q] != x);
+        const bool first = x != -1 && S.maxcp[j] <= lvl;   // no earlier row in play carries the same token here
         const unsigned mf = __ballot_sync(0xffffffffu, first);
         if (first) {
           const int pos = n + __popc(mf & ((1u << tid) - 1u));
           S.tried[pos] = x; S.kid_j[pos] = j; S.kid_node[pos] = cn;
+          S.kid_syn[pos] = S.csyn[j * D + lvl];
         }
         n += __popc(mf);
         __syncwarp();
       }
-      if (tid == 0) { S.iscr[38] = n; S.iscr[35] = first_member < 0 ? 0 : first_member; }
-    }
-    WB::sync();
-    const int n_kids = S.iscr[38], fi = S.iscr[35];   // fi: first row still matching the accepted prefix
-    if (cfg.lantern && tid < n_kids) {   // pull the children's neighbour-table rows towards L2 behind the row load
-      const int xk = S.tried[tid] - off;
-      if (xk >= 0 && xk < ncols) {
-        const uintptr_t a0 = (reinterpret_cast<uintptr_t>(P.in.nbr_table + (size_t)xk * cfg.table_cols) + 15) & ~uintptr_t(15);
-        const uintptr_t a1 = reinterpret_cast<uintptr_t>(P.in.nbr_table + (size_t)xk * cfg.table_cols + kk1) & ~uintptr_t(15);
-        if (a1 > a0) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a0), "r"((unsigned)(a1 - a0)));
+      if (tid == 0) S.iscr[38] = n;
+      TR(36);
+    };
+    // Once the list is published: pull the children's neighbour-table rows towards L2, and the logits rows of the first
+    // two children (the next row the walk needs if one of them is accepted; later children are prefetched when they are
+    // tried).  A bulk prefetch keeps its issuing lane busy for ~100 cycles, so the children are dealt out to the warps.
+    auto prefetch_children = [&]() {
+      if ((tid & 31) != 0) return;
+      const int n = S.iscr[38], w = tid >> 5, nw = NT >> 5;
+      if (w == nw - 1 && n > 0) prefetch_row(S.kid_node[0], lvl);
+      if (w == nw - 2 && n > 1) prefetch_row(S.kid_node[1], lvl);
+      if (!cfg.lantern) return;
+      for (int c = w; c < n; c += nw) {
+        const int xk = S.tried[c] - off;
+        if (xk >= 0 && xk < ncols) {
+          const uintptr_t a0 = (reinterpret_cast<uintptr_t>(P.in.nbr_table + (size_t)xk * cfg.table_cols) + 15) & ~uintptr_t(15);
+          const uintptr_t a1 = reinterpret_cast<uintptr_t>(P.in.nbr_table + (size_t)xk * cfg.table_cols + kk1) & ~uintptr_t(15);
+          if (a1 > a0) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a0), "r"((unsigned)(a1 - a0)));
+        }
       }
+    };
+    if (LNE > 0) {
+      set_distribution(node, false, [&]() {
+        if (staging) prologue();
+        list_children();
+      }, prefetch_children);
+    } else {
+      list_children();
+      WB::sync();
+      prefetch_children();
+      set_distribution(node, false, [] {}, [] {});
     }
-    int node = S.ri[fi * D + lvl - 1];
-    if (node < 0) node += T;
-    set_distribution(node, false);
+    const int n_kids = S.iscr[38];
+    TR(30 + lvl);
 
     bool accepted = false;
     for (int c = 0; c < n_kids && !accepted; ++c) {
       const int j = S.kid_j[c], cnode = S.kid_node[c], x = S.tried[c];
-      // If this child is accepted its own logits row is the next one the walk needs: pull it towards L2 now, behind
-      // the neighbour gather and the scan (a wasted prefetch costs 64 KiB of otherwise idle HBM bandwidth).
-      if (P.prefetch_rows && tid == 0 && cnode >= 0 && lvl + 1 < D) {
-        constexpr size_t eb = Elem<DT>::kBytes;
-        const int64_t nbase = (int64_t)b * cfg.item_stride + (int64_t)cnode * cfg.row_stride + col0;
-        const uintptr_t a0 = (reinterpret_cast<uintptr_t>(P.in.logits_cond) + nbase * eb + 15) & ~uintptr_t(15);
-        const uintptr_t a1 = (reinterpret_cast<uintptr_t>(P.in.logits_cond) + (nbase + ncols) * eb) & ~uintptr_t(15);
-        if (a1 > a0) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a0), "r"((unsigned)(a1 - a0)));
-        if (P.mix.has_uncond) {
-          const uintptr_t b0 = (reinterpret_cast<uintptr_t>(P.in.logits_uncond) + nbase * eb + 15) & ~uintptr_t(15);
-          const uintptr_t b1 = (reinterpret_cast<uintptr_t>(P.in.logits_uncond) + (nbase + ncols) * eb) & ~uintptr_t(15);
-          if (b1 > b0) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(b0), "r"((unsigned)(b1 - b0)));
-        }
-      }
+      if (c >= 2 && tid == 0) prefetch_row(cnode, lvl);   // the first two went out when the children were listed
+      TR(100 + c);
       const float r = uniform(draws++);
       float px = __fmul_rn(prob_of(x), scale);
       // only image tokens own a neighbour-table row; anything else (masked to probability 0 by every family's
       // tree_decoding) is tested on its own probability
       bool relaxable = x >= col0 && x < col1;
       if (P.lumina) {
-        if (is_syntax(x)) { px = 1.0f; relaxable = false; }
+        if (S.kid_syn[c]) { px = 1.0f; relaxable = false; }
         else if (!relaxable) px = 0.0f;
       }
       int idx = -1;
@@ -584,6 +884,7 @@ __global__ void __launch_bounds__(LNE > 0 ? kLazyThreads : kWalkThreads) walk_ke
       }
       // The relaxation only ever adds mass (px += cs[idx] >= 0): a candidate that passes on its own probability is
       // accepted whatever the neighbours hold, so their gather and scan are skipped for it.
+      TR(700 + c);
       const bool sure = r <= __fdiv_rn(px, qx);
       bool scan = cfg.lantern && relaxable && !sure;
       float bound = 0.f;
@@ -601,9 +902,9 @@ __global__ void __launch_bounds__(LNE > 0 ? kLazyThreads : kWalkThreads) walk_ke
       }
       if (scan) {
         // Prefix sums of the neighbour masses in fp64 (rounded to fp32 per prefix, like the CPU cumsum), in chunks of
-        // EPT * NT neighbours: each thread owns EPT consecutive neighbours, so the usual k = 1000 is one block scan for
-        // both CTA sizes (1024 threads x 1, 512 threads x 2).
-        const int ept = kk > NT ? 2 : 1;
+        // EPT * NT neighbours: each thread owns EPT <= 4 consecutive neighbours, so the usual k = 1000 is one block scan
+        // for both CTA sizes (1024 threads x 1, 256 threads x 4).
+        const int ept = min(4, (kk + NT - 1) / NT);
         const int span = NT * ept;
         double carry = 0.0;
         int n_ok = 0;
@@ -611,18 +912,23 @@ __global__ void __launch_bounds__(LNE > 0 ? kLazyThreads : kWalkThreads) walk_ke
           const int chunk = min(span, kk - base_t);
           if (tid == 0) S.iscr[39] = chunk;             // index (within the chunk) of the first sum above the bound
           const int t0 = base_t + tid * ept;
-          double v0 = 0.0, v1 = 0.0;
-          if (t0 < kk) v0 = (double)prob_of(__ldg(nb_row + t0) + off);
-          if (ept == 2 && t0 + 1 < kk) v1 = (double)prob_of(__ldg(nb_row + t0 + 1) + off);
+          double v[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            if (q < ept && t0 + q < kk) v[q] = (double)prob_of(__ldg(nb_row + t0 + q) + off);
+          const double mine = (v[0] + v[1]) + (v[2] + v[3]);
           double total;
-          const double incl1 = carry + block_scan_incl<WB>(v0 + v1, S.dscr, &total);   // prefix through the thread's last neighbour
-          const float cs0 = (float)((incl1 - v1) * (double)scale);
-          const float cs1 = (float)(incl1 * (double)scale);
+          double run = carry + block_scan_incl<WB>(mine, S.dscr, &total) - mine;   // prefix before the thread's first neighbour
           int fail = 0x7fffffff;                         // sums are non-decreasing: the failures form a suffix
-          if (t0 < kk && !(cs0 <= bound)) fail = tid * ept;
-          else if (ept == 2 && t0 + 1 < kk && !(cs1 <= bound)) fail = tid * ept + 1;
-          S.csv[tid * ept] = cs0;
-          if (ept == 2) S.csv[tid * ept + 1] = cs1;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            if (q < ept) {
+              run += v[q];
+              const float cs = (float)(run * (double)scale);
+              S.csv[tid * ept + q] = cs;
+              if (fail == 0x7fffffff && t0 + q < kk && !(cs <= bound)) fail = tid * ept + q;
+            }
+          }
           const int wfail = __reduce_min_sync(0xffffffffu, fail);
           if ((tid & 31) == 0 && wfail != 0x7fffffff) atomicMin(&S.iscr[39], wfail);
           WB::sync();
@@ -638,6 +944,7 @@ __global__ void __launch_bounds__(LNE > 0 ? kLazyThreads : kWalkThreads) walk_ke
           px = __fadd_rn(px, S.fscr[35]);
         }
       }
+      TR(800 + c);
       const float acp = __fdiv_rn(px, qx);
       if (r <= acp) {
         ++accept_length;
@@ -648,11 +955,13 @@ __global__ void __launch_bounds__(LNE > 0 ? kLazyThreads : kWalkThreads) walk_ke
         WB::sync();
         break;
       }
+      TR(200 + c);
       // ---------------- rejection: residual distribution ----------------
       dist_dirty = true;
       // every thread must have read this candidate's probabilities (px, first prefix sum) before any entry is zeroed:
       // the shortcuts above can reach this point without passing a barrier
       WB::sync();
+      TR(300 + c);
       const bool zero_nb = cfg.lantern && relaxable && idx != -1;
       double removed = 0.0;
       if (cfg.static_tree) {
@@ -709,14 +1018,21 @@ __global__ void __launch_bounds__(LNE > 0 ? kLazyThreads : kWalkThreads) walk_ke
         // gtp[x] = 0 and, if the candidate was relaxed, gtp[its k+1 nearest] = 0; atomicExch hands every entry's old
         // value to exactly one thread, whatever the table holds
         if (zero_nb) {
-          for (int tt = tid; tt < kk1; tt += NT) {
-            const int nbt = __ldg(nb_row + tt) + off - col0;
-            if (nbt >= 0 && nbt < ncols) removed += (double)atomicExch(&S.p[nbt], 0.f);
+          for (int t0 = tid; t0 < kk1; t0 += 4 * NT) {   // four table entries in flight per thread
+            int nbt[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) nbt[q] = t0 + q * NT < kk1 ? __ldg(nb_row + t0 + q * NT) + off - col0 : -1;
+            float old[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) old[q] = (nbt[q] >= 0 && nbt[q] < ncols) ? atomicExch(&S.p[nbt[q]], 0.f) : 0.f;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) removed += (double)old[q];
           }
         }
         if (x >= col0 && x < col1) { if (tid == 0) removed += (double)atomicExch(&S.p[x - col0], 0.f); }
         else if (x == extra_tok) p_extra = 0.f;
       }
+      TR(400 + c);
       double tot;
       bool resum = cfg.static_tree || !win_tot_valid;
       if (!resum) {
@@ -738,6 +1054,7 @@ __global__ void __launch_bounds__(LNE > 0 ? kLazyThreads : kWalkThreads) walk_ke
         win_tot = group_reduce<WB>((double)part, OpSum(), 0.0, S.dscr);
         win_tot_valid = !cfg.static_tree;
       }
+      TR(500 + c);
       tot = win_tot + (double)p_extra + (double)p_out * (double)(V - ncols - (extra_tok >= 0 ? 1 : 0));
       if ((float)tot == 0.f) {   // gtp = ones_like(gtp)
         for (int e = tid; e < ncols; e += NT) S.p[e] = 1.0f;
@@ -750,9 +1067,11 @@ __global__ void __launch_bounds__(LNE > 0 ? kLazyThreads : kWalkThreads) walk_ke
       }
       scale = __fdiv_rn(1.0f, (float)tot);   // gtp /= gtp.sum(), applied lazily
       adjust = true;
+      TR(600 + c);
     }
   }
 
+  TR(3);
   // ---------------- tail distribution ----------------
   const bool residual_tail = adjust && (accept_length != D);
   if (residual_tail) {
@@ -762,10 +1081,11 @@ __global__ void __launch_bounds__(LNE > 0 ? kLazyThreads : kWalkThreads) walk_ke
     if (node < 0) node += T;
     // the distribution of the last accepted node is often still in place, untouched (it was made for a level that had
     // no children to try): the reference recomputes the same softmax (:784-786)
-    if (!(dist_node == node && !dist_dirty && dist_raw == (P.tail_raw != 0))) set_distribution(node, P.tail_raw != 0);
+    if (!(dist_node == node && !dist_dirty && dist_raw == (P.tail_raw != 0))) set_distribution(node, P.tail_raw != 0, [] {}, [] {});
   }
   WB::sync();
 
+  TR(4);
   // ---------------- bonus token: inverse CDF, fp64, index order ----------------
   const float u = (cfg.bonus_uniform_last && P.in.uniforms)
                       ? P.in.uniforms[(size_t)b * cfg.n_uniforms + cfg.n_uniforms - 1]
@@ -788,24 +1108,38 @@ __global__ void __launch_bounds__(LNE > 0 ? kLazyThreads : kWalkThreads) walk_ke
     if (S.p[i] > 0.f) last_nz = i;
   }
   double wtot;
+  if (tid == 0) { S.iscr[36] = 0x7fffffff; S.iscr[37] = -1; }   // published by the barriers of the scan
   const double incl = block_scan_incl<WB>(loc, S.dscr, &wtot);
   const double massA = (double)p_out * (double)col0;
   const int n_suffix_uniform = V - col1 - ((extra_tok >= col1) ? 1 : 0);
   const double massB = (double)p_extra + (double)p_out * (double)n_suffix_uniform;
   const double total = massA + wtot + massB;
   const double target = (double)u * total;
-  WB::sync();
-  if (tid == 0) { S.iscr[36] = 0x7fffffff; S.iscr[37] = -1; }
-  WB::sync();
   {
-    double run = massA + incl - loc;
-    if (target >= run && target < run + loc) {
-      for (int i = i0; i < i1; ++i) {
-        run += (double)S.p[i];
-        if (run > target) { atomicMin(&S.iscr[36], i + col0); break; }
+    // the thread whose chunk holds the target hands the chunk to its warp: 32 entries per step, one warp scan each
+    const double run0 = massA + incl - loc;
+    const unsigned om = __ballot_sync(0xffffffffu, target >= run0 && target < run0 + loc);
+    if (om) {
+      const int src = __ffs(om) - 1, ln = tid & 31;
+      const int oi0 = __shfl_sync(0xffffffffu, i0, src), oi1 = __shfl_sync(0xffffffffu, i1, src);
+      double carry = __shfl_sync(0xffffffffu, run0, src);
+      int found = -1;
+      for (int c0 = oi0; c0 < oi1 && found < 0; c0 += 32) {
+        const int i = c0 + ln;
+        double v = i < oi1 ? (double)S.p[i] : 0.0;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const double n = __shfl_up_sync(0xffffffffu, v, o);
+          if (ln >= o) v += n;
+        }
+        const unsigned hm = __ballot_sync(0xffffffffu, i < oi1 && carry + v > target);
+        if (hm) found = c0 + __ffs(hm) - 1;
+        carry += __shfl_sync(0xffffffffu, v, 31);
       }
+      if (found >= 0 && ln == 0) atomicMin(&S.iscr[36], found + col0);
     }
-    if (last_nz >= 0) atomicMax(&S.iscr[37], last_nz + col0);
+    const int wl = __reduce_max_sync(0xffffffffu, last_nz);   // one shared-memory atomic per warp, not per thread
+    if ((tid & 31) == 0 && wl >= 0) atomicMax(&S.iscr[37], wl + col0);
   }
   WB::sync();
   int token = S.iscr[36];
@@ -824,6 +1158,7 @@ __global__ void __launch_bounds__(LNE > 0 ? kLazyThreads : kWalkThreads) walk_ke
     }
   }
 
+  TR(5);
   // ---------------- outputs ----------------
   const int a = accept_length - 1;
   if (tid == 0) {
@@ -841,6 +1176,14 @@ __global__ void __launch_bounds__(LNE > 0 ? kLazyThreads : kWalkThreads) walk_ke
     float* sp = P.out.sample_p + (size_t)b * V;
     for (int v = tid; v < V; v += NT) sp[v] = __fmul_rn(prob_of(v), scale);
   }
+  TR(6);
+#ifdef LANTERN_WALK_TRACE
+  if (tid == 0 && b < kTraceBlocks) {
+    g_trace[b][0] = tr_n;
+    g_trace[b][1] = draws;
+    for (int i = 0; i < 2 * tr_n; ++i) g_trace[b][2 + i] = tr_buf[i];
+  }
+#endif
 }
 
 // ----------------------------------------------------------------------------------------------
@@ -857,7 +1200,8 @@ static size_t walk_smem_bytes(const lantern_accept_cfg& c, int lazy_ne, bool spi
   o += (size_t)kWalkThreads * 4;
   o += (size_t)((c.n_rows + 4) & ~3) * 4;
   o += kMaxSib * 4 + 36 * 4 + 40 * 4;
-  o += (size_t)((c.n_paths + 3) & ~3) * 4 + 16;
+  o += 3 * (size_t)((c.n_paths + 3) & ~3) * 4 + 16;
+  o += 2 * (size_t)((c.n_paths * c.depth + 3) & ~3) * 4;
   o += 2 * 32 * 8 + 8;
   return o;
 }
@@ -872,7 +1216,7 @@ static int launch_all(const AcceptParams& P_in, cudaStream_t stream, int phases)
     // automatic policy (measured, profiles/sweep_r1.md): streaming every tree row pays off while the step is
     // latency-bound; from ~2K rows on, computing the statistics of the visited rows inside the walk is faster
     const int ne = c.ncols / kLazyThreads;
-    const bool lazy_ok = VEC && !P.do_topp && c.ncols % (4 * kLazyThreads) == 0 && (ne == 4 || ne == 8 || ne == 16 || ne == 32);
+    const bool lazy_ok = VEC && !P.do_topp && c.ncols % (4 * kLazyThreads) == 0 && (c.ncols == 2048 || c.ncols == 4096 || c.ncols == 8192 || c.ncols == 16384);
     phases = (lazy_ok && rows >= 2048) ? 6 : 3;
   }
   const int nquads = (c.ncols + 3) / 4;
@@ -996,30 +1340,30 @@ static int launch_all(const AcceptParams& P_in, cudaStream_t stream, int phases)
   int lazy_ne = 0;
   if ((phases & 4) && VEC && !P.do_topp && c.ncols % (4 * kLazyThreads) == 0) {
     const int ne = c.ncols / kLazyThreads;
-    if (ne == 4 || ne == 8 || ne == 16 || ne == 32) lazy_ne = ne;
+    if (c.ncols == 2048 || c.ncols == 4096 || c.ncols == 8192 || c.ncols == 16384) lazy_ne = ne;
   }
   if ((phases & 4) && !lazy_ne) {
     set_error("lazy statistics need a vector-aligned window of 2048/4096/8192/16384 columns and no top-p");
     return LANTERN_E_UNSUPPORTED;
   }
   const size_t smem = walk_smem_bytes(c, lazy_ne, P.p_spill != nullptr);
-  if (smem > 227 * 1024) {
+  if (smem + 8 * 1024 > 227 * 1024) {   // + the kernel's static arrays
     set_error("walk kernel needs %zu bytes of shared memory (> 227 KB): ncols too large", smem);
     return LANTERN_E_UNSUPPORTED;
   }
 #define LAUNCH_WALK(V, NE)                                                                          \
   do {                                                                                              \
     auto kern = walk_kernel<DT, V, NE>;                                                             \
-    if (smem > 48 * 1024)                                                                           \
+    if (smem > 36 * 1024)   /* the 48 KB default covers static + dynamic: the kernel has up to ~8 KB of static arrays */ \
       LANTERN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
     kern<<<c.n_items, (NE) > 0 ? kLazyThreads : kWalkThreads, smem, stream>>>(P);                   \
   } while (0)
   switch (lazy_ne) {
     case 0: LAUNCH_WALK(VEC, 0); break;
-    case 4: LAUNCH_WALK(true, 4); break;
-    case 8: LAUNCH_WALK(true, 8); break;
-    case 16: LAUNCH_WALK(true, 16); break;
-    default: LAUNCH_WALK(true, 32); break;
+    case 2048 / kLazyThreads: LAUNCH_WALK(true, 2048 / kLazyThreads); break;
+    case 4096 / kLazyThreads: LAUNCH_WALK(true, 4096 / kLazyThreads); break;
+    case 8192 / kLazyThreads: LAUNCH_WALK(true, 8192 / kLazyThreads); break;
+    default: LAUNCH_WALK(true, 16384 / kLazyThreads); break;
   }
 #undef LAUNCH_WALK
   LANTERN_CUDA(cudaGetLastError());
@@ -1031,7 +1375,7 @@ static int launch_all(const AcceptParams& P_in, cudaStream_t stream, int phases)
 using namespace lantern;
 
 // the walk's probability vector spills to global memory when the shared-memory carve-up would not fit
-static bool walk_spills(const lantern_accept_cfg& c) { return walk_smem_bytes(c, 0, false) > 227 * 1024; }
+static bool walk_spills(const lantern_accept_cfg& c) { return walk_smem_bytes(c, 0, false) + 8 * 1024 > 227 * 1024; }
 static size_t stats_bytes(const lantern_accept_cfg& c) {
   return ((size_t)c.n_items * (size_t)c.n_rows * sizeof(RowStats) + 255) & ~size_t(255);
 }
@@ -1188,3 +1532,12 @@ extern "C" int lantern_accept_phases(const lantern_accept_cfg* cfg, const lanter
   fill_params(P, cfg, in, out, workspace_dev);
   return dispatch_launch(P, static_cast<cudaStream_t>(stream), phases);
 }
+
+#ifdef LANTERN_WALK_TRACE
+// profiling builds only: per-CTA phase marks of the last walk launch ([blocks][2 + 2 * kTraceMax] int64: count, draws, pairs)
+extern "C" LANTERN_API int lantern_debug_walk_trace(long long* host, int max_blocks) {
+  cudaDeviceSynchronize();
+  const int n = max_blocks < kTraceBlocks ? max_blocks : kTraceBlocks;
+  return (int)cudaMemcpyFromSymbol(host, g_trace, sizeof(long long) * (size_t)n * (2 * kTraceMax + 2));
+}
+#endif

@@ -302,13 +302,15 @@ __device__ __forceinline__ RowStats raw_row_stats(const AcceptParams& P, int b, 
 // of select.cuh as before.  Returns true (and writes nothing) when every live column is -inf: a pre-masked one-hot
 // row (see set_distribution).
 constexpr int kLazyListMax = 128;
-struct LazySmem {
+struct __align__(16) LazySmem {
   float4 mom[kLazyThreads / 32];        // per-warp (sum, sum of squares, min, max)
   int4 cnt[kLazyThreads / 32];          // per-warp (elements above the bracket, parked elements, bits of their exp-sum, -)
   unsigned wh[kLazyThreads / 32][8];    // per-warp counts of the 16 bracket fields, two 16-bit counts per word
+  float list[kLazyListMax];             // the members of the field that holds the k-th largest value (16-byte aligned: the
+                                        // compiler reads it with vector loads)
   float part[kLazyThreads / 32];        // per-warp kept mass
   float thr;
-  float list[kLazyListMax];
+  float pad[3];
 };
 
 template <int DT, int NE, class Hook, class Post>
@@ -1049,9 +1051,11 @@ __global__ void __launch_bounds__(LNE > 0 ? kLazyThreads : kWalkThreads) walk_ke
       }
       if (resum) {
         WB::sync();
-        float part = 0.f;
-        for (int e = tid; e < ncols; e += NT) part += S.p[e];
-        win_tot = group_reduce<WB>((double)part, OpSum(), 0.0, S.dscr);
+        // fp64 from the first add: later rejections subtract their exact removed mass from this sum, so an fp32
+        // partial (1e-7 of the whole window) would be amplified by whole / remaining mass in the residual's scale
+        double part = 0.0;
+        for (int e = tid; e < ncols; e += NT) part += (double)S.p[e];
+        win_tot = group_reduce<WB>(part, OpSum(), 0.0, S.dscr);
         win_tot_valid = !cfg.static_tree;
       }
       TR(500 + c);

@@ -96,6 +96,16 @@ def main():
         stream_rows()
         accept(dict(family="vanilla", ncols=65536, cfg=False, lantern=False, top_k=50, boost=13.0, total_tokens=8, seed=700))
         one_call()
+        # round 2, lazy walk rewritten for latency (256 threads, children listed / tree staged inside the row's load
+        # shadow, atomic-free bracket select): every row width it is instantiated for, a deep tree, a static tree,
+        # rows that miss the bracket (heavy ties -> slow selectors), no top-k at all
+        accept(dict(family="llamagen", ncols=2048, top_k=300, lantern_k=100, boost=11.0, total_tokens=59), phases=6)
+        accept(dict(family="anole", ncols=8192, top_k=2000, lantern_k=1000, depth=5, total_tokens=59, boost=13.0, seed=900), phases=6)
+        accept(dict(family="llamagen", ncols=16384, top_k=1000, lantern_k=1000, total_tokens=26, boost=13.0, seed=950), phases=6)
+        accept(dict(family="llamagen", ncols=2048, top_k=300, lantern_k=20, lantern_delta=5.0,
+                    static_tree="mc_sim_7b_63", seed=500), phases=6)
+        accept(dict(family="llamagen", ncols=2048, top_k=0, lantern_k=100, boost=11.0, seed=980), phases=6)
+        accept(dict(family="lumina_mgpt", ncols=4096, top_k=500, lantern_k=100, depth=5, newline_depth=2, seed=990), phases=6)
         print("accept ok", flush=True)
     if "neighbors" in which:
         for N, d, K in ((1024, 8, 65), (512, 256, 33), (300, 8, 299), (2304, 8, 1001)):

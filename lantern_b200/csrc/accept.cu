@@ -313,6 +313,40 @@ struct __align__(16) LazySmem {
   float pad[3];
 };
 
+// one pass of the CFG mix + moments over the thread's raw row values (unrolled: the values sit in registers), the mixed
+// logits stored to the thread's own slots of `p`.  HAS_UNCOND / DO_TEMP are compile-time here: with run-time flags
+// the compiler emits both arms for every pair, which tripled the code of this pass.
+template <int NQ, int NT, bool HAS_UNCOND, bool DO_TEMP>
+__device__ __forceinline__ void lazy_lift(const float (&cc)[NQ][4], const float (&uu)[NQ][4], const MixParams& mix_in,
+                                          float* p, int tid, float& fsum, float& fsq, float& fmx) {
+  MixParams mix = mix_in;
+  mix.has_uncond = HAS_UNCOND ? 1 : 0;
+  mix.do_temp = DO_TEMP ? 1 : 0;
+  uint64_t sum2 = pack2(0.f, 0.f), sq2 = pack2(0.f, 0.f);
+  float mx = -INFINITY;
+#pragma unroll
+  for (int q = 0; q < NQ; ++q) {
+    float4 o;
+    const uint64_t a2 = mix_temper2(cc[q][0], cc[q][1], uu[q][0], uu[q][1], mix);
+    const uint64_t b2 = mix_temper2(cc[q][2], cc[q][3], uu[q][2], uu[q][3], mix);
+    unpack2(a2, o.x, o.y);
+    unpack2(b2, o.z, o.w);
+    sum2 = add2(sum2, a2); sq2 = fma2(a2, a2, sq2);
+    sum2 = add2(sum2, b2); sq2 = fma2(b2, b2, sq2);
+    mx = fmaxf(mx, fmaxf(fmaxf(o.x, o.y), fmaxf(o.z, o.w)));
+    *reinterpret_cast<float4*>(p + (q * NT + tid) * 4) = o;
+  }
+  float a0, a1;
+  unpack2(sum2, a0, a1); fsum = a0 + a1;
+  unpack2(sq2, a0, a1); fsq = a0 + a1;
+  fmx = mx;
+}
+
+// Round 2, second form.  ncu on the first latency-oriented version (registers-resident row, every pass fully unrolled)
+// showed the walk stalled on instruction fetch above everything else (no_instruction 4.2 warps per issue, issue slots
+// 18 % busy): the kernel executes ~8000 instructions per warp exactly once, so it runs at the rate the instruction
+// cache can be refilled from L2.  The row therefore lives in shared memory - in `p`, every thread touching only its
+// own slots, so no barrier is involved - and the per-element passes are rolled loops of a few dozen instructions.
 template <int DT, int NE, class Hook, class Post>
 __device__ __forceinline__ bool lazy_probs(const AcceptParams& P, int b, int node, bool raw, float* p, float* park,
                                            LazySmem& lz, SelectSmem& sm, float& z_run, float& win_run, Hook&& hook,
@@ -325,37 +359,26 @@ __device__ __forceinline__ bool lazy_probs(const AcceptParams& P, int b, int nod
   const int64_t base = (int64_t)b * cfg.item_stride + (int64_t)node * cfg.row_stride + cfg.col0;
   MixParams mix = P.mix;
   if (raw) mix.do_temp = 0;
-  // ---- the row's loads go out first; nothing below touches them until the hook has run ----
-  float cc[NQ][4], uu[NQ][4];
-#pragma unroll
-  for (int q = 0; q < NQ; ++q) {
-    const int e0 = (q * NT + tid) * 4;
-    Elem<DT>::load4(P.in.logits_cond, base + e0, cc[q]);
-    if (mix.has_uncond) Elem<DT>::load4(P.in.logits_uncond, base + e0, uu[q]);
-    else { uu[q][0] = uu[q][1] = uu[q][2] = uu[q][3] = 0.f; }
-  }
-  hook();
-  TR(39);
-  // The SM handles 128 lanes per clock, so every instruction spent per element costs 64 cycles of an 8192-column row:
-  // the passes below are written for instruction count (packed fp32 pairs, predicated adds, a running store pointer).
-  float s[NE];
-  float fsum, fsq, fmx = -INFINITY;
+  float fsum, fsq, fmx;
   {
-    uint64_t sum2 = pack2(0.f, 0.f), sq2 = pack2(0.f, 0.f);
+    // ---- the row's loads go out first; nothing touches them until the hook has run ----
+    float cc[NQ][4], uu[NQ][4];
 #pragma unroll
     for (int q = 0; q < NQ; ++q) {
-#pragma unroll
-      for (int j = 0; j < 4; j += 2) {
-        const uint64_t v2 = mix_temper2(cc[q][j], cc[q][j + 1], uu[q][j], uu[q][j + 1], mix);
-        unpack2(v2, s[q * 4 + j], s[q * 4 + j + 1]);
-        sum2 = add2(sum2, v2);
-        sq2 = fma2(v2, v2, sq2);
-        fmx = fmaxf(fmx, fmaxf(s[q * 4 + j], s[q * 4 + j + 1]));
-      }
+      const int e0 = (q * NT + tid) * 4;
+      Elem<DT>::load4(P.in.logits_cond, base + e0, cc[q]);
+      if (mix.has_uncond) Elem<DT>::load4(P.in.logits_uncond, base + e0, uu[q]);
+      else { uu[q][0] = uu[q][1] = uu[q][2] = uu[q][3] = 0.f; }
     }
-    float a0, a1;
-    unpack2(sum2, a0, a1); fsum = a0 + a1;
-    unpack2(sq2, a0, a1); fsq = a0 + a1;
+    hook();
+    TR(39);
+    if (mix.has_uncond) {
+      if (mix.do_temp) lazy_lift<NQ, NT, true, true>(cc, uu, mix, p, tid, fsum, fsq, fmx);
+      else lazy_lift<NQ, NT, true, false>(cc, uu, mix, p, tid, fsum, fsq, fmx);
+    } else {
+      if (mix.do_temp) lazy_lift<NQ, NT, false, true>(cc, uu, mix, p, tid, fsum, fsq, fmx);
+      else lazy_lift<NQ, NT, false, false>(cc, uu, mix, p, tid, fsum, fsq, fmx);
+    }
   }
   TR(40);
   {
@@ -381,7 +404,7 @@ __device__ __forceinline__ bool lazy_probs(const AcceptParams& P, int b, int nod
   if (fmx == -INFINITY) return true;   // block-uniform
   TR(41);
   const ExpShift ex(fmx);
-  float ev[NE];
+  float4* const mine = reinterpret_cast<float4*>(p) + tid;   // the thread's quads: mine[q * NT], q < NQ
   float thr = -INFINITY, tot = 0.f;
   bool have_tot = false;
   if (P.do_topk && !raw) {
@@ -397,32 +420,30 @@ __device__ __forceinline__ bool lazy_probs(const AcceptParams& P, int b, int nod
       const float lo = mean + (z_run - win_run) * sd, hi = mean + (z_run + win_run) * sd;
       const Classifier cls = make_classifier(lo, hi);   // 16 fields; the bracket itself is tiled by fields 1..14
       const bool fast = finite && lo < hi && isfinite(cls.scale) && isfinite(cls.bias23);
-      // One sweep: exp of every element, count and exp-sum of the elements above the bracket, the elements inside it
-      // parked in the thread's private shared-memory column (branch-free: every element is stored at the running slot,
-      // only an element inside the bracket keeps it).  No shared-memory atomics anywhere in this routine: they cost
-      // two cycles per lane on this machine, which made a 64-field atomic histogram the most expensive step of the row.
-      int above = 0, slot = 0;
-      float sum_ab = 0.f;
-      if (fast) {
-        float* pp = park + tid;
-#pragma unroll
-        for (int e = 0; e < NE; ++e) {
-          const float v = s[e];
-          const float x = ex(v);
-          ev[e] = x;
-          const bool ab = v > hi;
-          if (ab) { sum_ab += x; ++above; }
-          *pp = v;
-          if (!ab && v >= lo) pp += NT;
-        }
-        slot = (int)(pp - (park + tid)) / NT;
-      } else {
-#pragma unroll
-        for (int e = 0; e < NE; ++e) ev[e] = ex(s[e]);
-      }
       slow = !fast;
       if (fast) {
-        // the thread's parked elements by field: sixteen 8-bit counters in two registers (a thread parks <= NE <= 32)
+        // One sweep: count and exp-sum of the elements above the bracket, the elements inside it parked in the thread's
+        // private shared-memory column (branch-free: every element is stored at the running slot, only an element
+        // inside the bracket keeps it).  No shared-memory atomics anywhere in this routine: they cost two cycles per
+        // lane on this machine, which made an atomic histogram the most expensive step of the row.
+        int above = 0;
+        float sum_ab = 0.f;
+        float* pp = park + tid;
+#pragma unroll 1
+        for (int q = 0; q < NQ; ++q) {
+          const float4 v4 = mine[q * NT];
+          const float vv[4] = {v4.x, v4.y, v4.z, v4.w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float v = vv[j];
+            const bool ab = v > hi;
+            if (ab) { sum_ab += ex(v); ++above; }
+            *pp = v;
+            if (!ab && v >= lo) pp += NT;
+          }
+        }
+        const int slot = (int)(pp - (park + tid)) / NT;
+        // the thread's parked elements by field: sixteen 8-bit counters in two registers (a thread parks <= NE <= 64)
         unsigned long long ca = 0ull, cb = 0ull;
         for (int i = 0; i < slot; ++i) {
           const unsigned f = cls(park[i * NT + tid]);
@@ -478,8 +499,8 @@ __device__ __forceinline__ bool lazy_probs(const AcceptParams& P, int b, int nod
             if (f + o < 16) incl += n;
           }
           const unsigned above_f = incl - cf;
-          const bool mine = above_f < (unsigned)krem && above_f + cf >= (unsigned)krem;
-          const unsigned owner_mask = __ballot_sync(kFull, mine) & 0xffffu;
+          const bool own = above_f < (unsigned)krem && above_f + cf >= (unsigned)krem;
+          const unsigned owner_mask = __ballot_sync(kFull, own) & 0xffffu;
           const int F = owner_mask ? __ffs(owner_mask) - 1 : -1;
           const int above2 = (int)__shfl_sync(kFull, above_f, F >= 0 ? F : 0);
           const int cntF = (int)__shfl_sync(kFull, cf, F >= 0 ? F : 0);
@@ -543,26 +564,34 @@ __device__ __forceinline__ bool lazy_probs(const AcceptParams& P, int b, int nod
       }
     }
     TR(42);
-    if (slow) {   // block-uniform
+    if (slow) {   // block-uniform; rare: the exact selectors of select.cuh work on a register copy of the row
       __syncthreads();
       float tmp[NE];
       float fmn = INFINITY;   // the fast path has no use for the row minimum
 #pragma unroll
-      for (int e = 0; e < NE; ++e) { tmp[e] = s[e]; fmn = fminf(fmn, s[e]); }
+      for (int q = 0; q < NQ; ++q) {
+        const float4 v4 = mine[q * NT];
+        tmp[q * 4 + 0] = v4.x; tmp[q * 4 + 1] = v4.y; tmp[q * 4 + 2] = v4.z; tmp[q * 4 + 3] = v4.w;
+        fmn = fminf(fmn, fminf(fminf(v4.x, v4.y), fminf(v4.z, v4.w)));
+      }
       fmn = -block_reduce(-fmn, OpMaxF(), -INFINITY, sm.f4[0]);
       thr = select_slow<NE>(tmp, k, fmn, fmx, sm);
       __syncthreads();
     }
     const float z_obs = (thr - mean) / sd;
     if (isfinite(z_obs)) { z_run = z_obs; win_run = P.win_sd; }   // a walk visits too few rows to adapt the width
-  } else {
-#pragma unroll
-    for (int e = 0; e < NE; ++e) ev[e] = ex(s[e]);
   }
+  TR(43);
   if (!have_tot) {
     float part = 0.f;
-#pragma unroll
-    for (int e = 0; e < NE; ++e) part += (s[e] >= thr) ? ev[e] : 0.f;
+#pragma unroll 1
+    for (int q = 0; q < NQ; ++q) {
+      const float4 v4 = mine[q * NT];
+      part += v4.x >= thr ? ex(v4.x) : 0.f;
+      part += v4.y >= thr ? ex(v4.y) : 0.f;
+      part += v4.z >= thr ? ex(v4.z) : 0.f;
+      part += v4.w >= thr ? ex(v4.w) : 0.f;
+    }
     part = warp_reduce(part, OpSum());
     __syncthreads();
     if (lane == 0) lz.part[warp] = part;
@@ -573,15 +602,15 @@ __device__ __forceinline__ bool lazy_probs(const AcceptParams& P, int b, int nod
   }
   const float inv = __fdiv_rn(1.0f, tot);
   TR(44);
-#pragma unroll
+  // logits -> probabilities in place (the exp is taken a second time here: cheaper than carrying it)
+#pragma unroll 2
   for (int q = 0; q < NQ; ++q) {
-    const int e0 = (q * NT + tid) * 4;
-    float4 o;
-    o.x = s[q * 4 + 0] >= thr ? __fmul_rn(ev[q * 4 + 0], inv) : 0.f;
-    o.y = s[q * 4 + 1] >= thr ? __fmul_rn(ev[q * 4 + 1], inv) : 0.f;
-    o.z = s[q * 4 + 2] >= thr ? __fmul_rn(ev[q * 4 + 2], inv) : 0.f;
-    o.w = s[q * 4 + 3] >= thr ? __fmul_rn(ev[q * 4 + 3], inv) : 0.f;
-    *reinterpret_cast<float4*>(p + e0) = o;
+    float4 v4 = mine[q * NT];
+    v4.x = v4.x >= thr ? __fmul_rn(ex(v4.x), inv) : 0.f;
+    v4.y = v4.y >= thr ? __fmul_rn(ex(v4.y), inv) : 0.f;
+    v4.z = v4.z >= thr ? __fmul_rn(ex(v4.z), inv) : 0.f;
+    v4.w = v4.w >= thr ? __fmul_rn(ex(v4.w), inv) : 0.f;
+    mine[q * NT] = v4;
   }
   return false;
 }

@@ -47,7 +47,7 @@ def default_params(**kw) -> dict:
     p = dict(family="llamagen", ncols=None, tree="eagle2", total_tokens=59, depth=4, seed=0,
              lantern=True, lantern_k=1000, lantern_delta=0.1, temperature=1.0, top_k=2000, top_p=1.0,
              cfg_scale=3.0, cfg=True, boost=13.0, static_tree=None, newline_depth=-1, sharp=1.0, table_seed=0,
-             newline_junk=False)
+             newline_junk=False, dup_siblings=0)
     p.update(kw)
     return p
 
@@ -91,6 +91,20 @@ def build(params: dict) -> Built:
         static = O.StaticDraft(cart_prob, ssyn.op, tbuf["p_indices"], tbuf["b_indices"], tree.tokens)
     else:
         synth.assign_tokens(seed, tree, lo, hi)
+        if p["dup_siblings"]:
+            # Duplicate tokens among siblings (never produced by a top-k drafter, but the reference dedups the children
+            # of a node by TOKEN, ea_model_llamagen.py:728-739, so two subtrees can sit behind one accepted token): the
+            # later sibling takes an earlier sibling's token.
+            r = synth.hash_u64(seed, 4 * T, stream=91)
+            done = 0
+            for t in range(4 * T):
+                i = 1 + int(r[t] % np.uint64(T - 1))
+                sibs = [j for j in range(1, i) if tree.parent[j] == tree.parent[i] and tree.tokens[j] != tree.tokens[i]]
+                if sibs:
+                    tree.tokens[i] = tree.tokens[sibs[int(r[(t + 1) % (4 * T)] % np.uint64(len(sibs)))]]
+                    done += 1
+                    if done >= p["dup_siblings"]:
+                        break
 
     if fam.lumina:
         row_kinds = np.zeros(T, dtype=np.int8)

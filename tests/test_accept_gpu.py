@@ -425,3 +425,32 @@ def test_random_configurations_match_oracle(chunk):
                     R.compare(res, i, o)
                 except AssertionError as e:
                     raise AssertionError(f"params={p} seed={built[i].params['seed']} phases={phases}: {e}") from e
+
+
+@pytest.mark.parametrize("family,kw", [("llamagen", dict(ncols=2048, top_k=300, lantern_k=100, boost=10.0)),
+                                       ("lumina_mgpt", dict(ncols=4096, top_k=500, lantern_k=100, depth=5, boost=10.0)),
+                                       ("anole", dict(ncols=2048, top_k=400, lantern_k=64, boost=9.0, tree="random"))])
+def test_duplicate_sibling_tokens(family, kw):
+    """The reference lists the children of a node by TOKEN (`candidates_set`, ea_model_llamagen.py:728-739): siblings
+    that carry the same token are one candidate, and after its acceptance the rows of both subtrees stay in play.  The
+    walk's dedup is a static table (longest token prefix a row shares with an earlier row); synthetic trees never
+    repeat a token among siblings, so this case builds them on purpose.  Both schedules, every prompt against its oracle."""
+    built, orcs, seed = [], [], 31000
+    while len(built) < 8:
+        b = C.build(dict(family=family, seed=seed, total_tokens=40, dup_siblings=6, **kw))
+        seed += 1
+        toks, par = b.tree.tokens, b.tree.parent
+        assert any(toks[i] == toks[j] for i in range(1, b.tree.T) for j in range(1, i) if par[i] == par[j])
+        o = C.oracle_step(b)
+        if o.margin >= MARGIN:
+            built.append(b)
+            orcs.append(o)
+    def through_duplicate(b, o):   # the accepted path passes a token that a sibling carries too
+        toks, par = b.tree.tokens, b.tree.parent
+        return any(j != int(n) and par[j] == par[int(n)] and toks[j] == toks[int(n)]
+                   for n in o.select_indices[1:] for j in range(1, b.tree.T))
+    assert sum(through_duplicate(b, o) for b, o in zip(built, orcs)) >= 2
+    for phases in (3, 6):
+        res = R.run_cases(built, phases=phases)
+        for i, o in enumerate(orcs):
+            R.compare(res, i, o)

@@ -158,8 +158,8 @@ LANTERN_API int lantern_accept_fused(const lantern_accept_cfg* cfg, const lanter
 
 /* The same step with an explicit schedule.  phases bit 0: per-row statistics kernel over every tree row (streamed,
  * HBM-bound); bit 1: walk kernel; bit 2: lazy - the walk computes the statistics of the rows it visits itself (no
- * streamed kernel; needs a 2048/4096/8192/16384-column window and no top-p); bit 3: automatic - streamed below
- * 2048 tree rows in the batch, lazy from there on when eligible; bit 4: no speculative row prefetch in the walk (used
+ * streamed kernel; needs a 2048/4096/8192/16384-column window and no top-p); bit 3: automatic - lazy when eligible
+ * and the batch holds at least 2048 tree rows or the trees at least 48 rows each, streamed otherwise; bit 4: no speculative row prefetch in the walk (used
  * when the logits are read over PCIe).  3 is lantern_accept_fused, 6 lazy, 8 automatic,
  * 1 times the HBM-bound kernel on its own (bench.py).  Results are identical in every schedule. */
 LANTERN_API int lantern_accept_phases(const lantern_accept_cfg* cfg, const lantern_accept_in* in,

@@ -1250,7 +1250,10 @@ static int launch_all(const AcceptParams& P_in, cudaStream_t stream, int phases)
     // latency-bound; from ~2K rows on, computing the statistics of the visited rows inside the walk is faster
     const int ne = c.ncols / kLazyThreads;
     const bool lazy_ok = VEC && !P.do_topp && c.ncols % (4 * kLazyThreads) == 0 && (c.ncols == 2048 || c.ncols == 4096 || c.ncols == 8192 || c.ncols == 16384);
-    phases = (lazy_ok && rows >= 2048) ? 6 : 3;
+    // (round 2, rewritten lazy walk: from ~48 tree rows per prompt on it is no slower at any batch size, cold or warm -
+    // profiles/r2/sweep_r2.md, profiles/r2/auto_policy_ab.txt; tiny trees visit most of their rows and keep the
+    // streamed form, which spreads them over the SMs)
+    phases = (lazy_ok && (rows >= 2048 || c.n_rows >= 48)) ? 6 : 3;
   }
   const int nquads = (c.ncols + 3) / 4;
   // Thread/element split.  Generic mode: 256 threads up to 8192 columns, 512 beyond.  Fast (TMA-staged) modes:

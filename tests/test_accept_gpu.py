@@ -240,8 +240,10 @@ def test_lazy_statistics_mode(family, kw):
 
 def test_automatic_schedule_matches_both():
     """phases = 8: the library picks streamed or lazy per batch; either way the results are the oracle's.  Covers a
-    window that is not lazy-eligible (2048 columns), a small batch (streamed) and one past the 2048-row switch."""
+    generic window, small trees in a small batch (streamed), 59-row trees in a small batch (lazy since round 2: from 48
+    rows per prompt on) and a batch past the 2048-row switch."""
     for kw, n in ((dict(family="llamagen", ncols=2048, top_k=300, lantern_k=100), 3),
+                  (dict(family="lumina_mgpt", ncols=4096, top_k=500, lantern_k=100, depth=5, total_tokens=26), 3),
                   (dict(family="lumina_mgpt", ncols=4096, top_k=500, lantern_k=100, depth=5), 3),
                   (dict(family="lumina_mgpt", ncols=4096, top_k=500, lantern_k=100, depth=5), 40)):
         built, orcs, seed = [], [], 47000

@@ -287,17 +287,18 @@ __device__ __forceinline__ RowStats raw_row_stats(const AcceptParams& P, int b, 
 }
 
 // Lazy mode (phases bit 2): statistics of a visited row computed inside the walk CTA, straight from the logits,
-// and the probability vector written from registers (one global read of the row instead of two, and no
-// statistics for the ~85 % of tree rows the walk never visits).  Same arithmetic as the streamed kernels.
+// and the probability vector written in place (one global read of the row instead of two, and no statistics for the
+// ~85 % of tree rows the walk never visits).  Same arithmetic as the streamed kernels.
 //
 // The walk waits for every row it visits, so this routine is built for latency, not throughput (round 2: the first
-// version spent 13 block barriers and two MUFU passes per row, ~7800 cycles after the loads had landed):
-//   * four barriers on the common path: moments, bracket counts + histogram, candidate list, kept mass;
-//   * exp() once per element (the kept-mass sum and the probability vector use the same register copy);
-//   * everything a single warp used to do behind a barrier (histogram scan, exact ranking of the handful of
-//     candidates) is done by every warp redundantly from the same shared-memory data - no broadcast barrier;
+// version spent 13 block barriers per row, ~7800 cycles after the loads had landed):
+//   * four barriers on the common path: moments; bracket counts; candidate list + kept mass of the fields above the
+//     target field; threshold;
+//   * no shared-memory atomics; the scan of the 16 field counts is done by every warp itself (no broadcast barrier),
+//     the ranking of the candidates one candidate per thread;
 //   * `hook` runs between issuing the row's loads and their first use: the walk lists the children of the current node
-//     (one warp) inside the load shadow; `post` runs behind the first barrier, where the hook's results are visible.
+//     (one warp) inside the load shadow; `post` runs behind the first barrier, where the hook's results are visible;
+//   * the row lives in shared memory and the per-element passes are rolled loops (see lazy_probs below).
 // Rows the moment bracket misses (non-Gaussian rows, heavy ties, non-finite values) take the exact tier-2/3 selectors
 // of select.cuh as before.  Returns true (and writes nothing) when every live column is -inf: a pre-masked one-hot
 // row (see set_distribution).
@@ -615,7 +616,7 @@ __device__ __forceinline__ bool lazy_probs(const AcceptParams& P, int b, int nod
   return false;
 }
 
-// LNE > 0: lazy form (512 threads, the walk computes the statistics of the rows it visits); LNE == 0: the walk behind
+// LNE > 0: lazy form (kLazyThreads threads, the walk computes the statistics of the rows it visits); LNE == 0: the walk behind
 // the streamed row-statistics kernel (1024 threads).
 template <int DT, bool VEC, int LNE>
 __global__ void __launch_bounds__(LNE > 0 ? kLazyThreads : kWalkThreads) walk_kernel(const AcceptParams P) {

@@ -684,7 +684,9 @@ __global__ void __launch_bounds__(LNE > 0 ? kLazyThreads : kWalkThreads) walk_ke
       else uv = philox_uniform(cfg.philox_seed, cfg.philox_step, (uint32_t)b, (uint32_t)i);
       S.uni[i] = uv;
     }
+    TR(21);
     WB::sync();
+    TR(22);
     for (int i = tid; i < L * D; i += NT) {
       const int n = S.ri[i];
       const int x = n >= 0 ? S.tok[n] : -1;
@@ -695,6 +697,7 @@ __global__ void __launch_bounds__(LNE > 0 ? kLazyThreads : kWalkThreads) walk_ke
       S.csyn[i] = syn;
     }
     WB::sync();
+    TR(23);
     {
       const int root_tok = cand(0, 0);
       for (int j = tid; j < L; j += NT) member[j] = cand(j, 0) == root_tok ? 1 : 0;
@@ -703,7 +706,7 @@ __global__ void __launch_bounds__(LNE > 0 ? kLazyThreads : kWalkThreads) walk_ke
     // ea_model_llamagen.py:728-739).  The rows in play at level l all carry the accepted tokens at levels < l, so row
     // j repeats an earlier row's token at level l exactly when an earlier row shares j's token prefix through level l:
     // a property of the tree alone.  maxcp[j] = the longest token prefix row j shares with any earlier row.
-    for (int j = tid >> 5; j < L; j += NT >> 5) {
+    for (int j = tid >> 5; j < L; j += NT >> 5) {   // one warp per row, the lanes take the earlier rows
       int longest = 0;
       for (int jj = tid & 31; jj < j; jj += 32) {
         int cp = D;
@@ -714,7 +717,9 @@ __global__ void __launch_bounds__(LNE > 0 ? kLazyThreads : kWalkThreads) walk_ke
       longest = __reduce_max_sync(0xffffffffu, longest);
       if ((tid & 31) == 0) S.maxcp[j] = longest;
     }
+    TR(24);
     WB::sync();
+    TR(25);
   };
   const bool defer_prologue = LNE > 0 && D > 1;
   if (!defer_prologue) prologue();

@@ -21,6 +21,7 @@ KT, KB = 120, 256
 NAMES = {1: "start", 2: "prologue done", 3: "levels done", 4: "tail dist done", 5: "bonus done", 6: "outputs done"}
 def name(t):
     if t in NAMES: return NAMES[t]
+    if 21 <= t <= 25: return "  prologue: " + {21: "loads issued / uniforms", 22: "staged (barrier)", 23: "token table", 24: "dedup table", 25: "barrier"}[t]
     if t in (35, 36, 37): return "  " + {35: "node known", 36: "children listed", 37: "prefetches issued"}[t]
     if t == 39: return "  row loads issued + hook done"
     if 10 <= t < 20: return f"L{t-10} begin"

@@ -924,7 +924,10 @@ __global__ void __launch_bounds__(LNE > 0 ? kLazyThreads : kWalkThreads) walk_ke
       // The relaxation only ever adds mass (px += cs[idx] >= 0): a candidate that passes on its own probability is
       // accepted whatever the neighbours hold, so their gather and scan are skipped for it.
       TR(700 + c);
-      const bool sure = r <= __fdiv_rn(px, qx);
+      // (qx is exactly 1 on a dynamic tree and x / 1 = x: the IEEE division sequences are skipped there - on this
+      // one-shot instruction stream every instruction that is not executed counts)
+      auto over_q = [&](float v) -> float { return cfg.static_tree ? __fdiv_rn(v, qx) : v; };
+      const bool sure = r <= over_q(px);
       bool scan = cfg.lantern && relaxable && !sure;
       float bound = 0.f;
       if (scan) {
@@ -933,7 +936,7 @@ __global__ void __launch_bounds__(LNE > 0 ? kLazyThreads : kWalkThreads) walk_ke
         // The added mass never exceeds the bound (cs[idx] <= bound, rounding is monotone), so a draw above
         // (px + bound) / qx is a rejection whatever the neighbours hold.  The residual update then only needs to know
         // whether any neighbour was aggregated (idx != -1), i.e. whether the first prefix sum is within the bound.
-        if (r > __fdiv_rn(__fadd_rn(px, bound), qx)) {
+        if (r > over_q(__fadd_rn(px, bound))) {
           scan = false;
           const float cs0 = (float)((double)prob_of(__ldg(nb_row) + off) * (double)scale);
           idx = (kk > 0 && cs0 <= bound) ? 0 : -1;
@@ -984,7 +987,7 @@ __global__ void __launch_bounds__(LNE > 0 ? kLazyThreads : kWalkThreads) walk_ke
         }
       }
       TR(800 + c);
-      const float acp = __fdiv_rn(px, qx);
+      const float acp = over_q(px);
       if (r <= acp) {
         ++accept_length;
         best = j;

@@ -412,14 +412,20 @@ __device__ __forceinline__ bool lazy_probs(const AcceptParams& P, int b, int nod
     // a finite sum of squares means every element is finite (a constant row ends on the slow path: its bracket is
     // empty or holds the whole row)
     const bool finite = isfinite(fmx) && isfinite(fsq);
-    const float inv_n = 1.0f / (float)cfg.ncols;
+    // mean, sd, the bracket and the field scale only steer the search (any values keep it exact, and they are the same
+    // in every thread): approximate reciprocal / square root instead of the IEEE sequences - on this one-shot
+    // instruction stream ~80 instructions per row
+    const float inv_n = P.inv_ncols;
     const float mean = fsum * inv_n;
-    const float sd = sqrtf(fmaxf(fsq * inv_n - mean * mean, 0.f));
+    const float var = fmaxf(fsq * inv_n - mean * mean, 0.f);
+    const float sd = var > 0.f ? var * rsqrtf(var) : 0.f;
     const int k = cfg.top_k;
     bool slow = false;
     {
       const float lo = mean + (z_run - win_run) * sd, hi = mean + (z_run + win_run) * sd;
-      const Classifier cls = make_classifier(lo, hi);   // 16 fields; the bracket itself is tiled by fields 1..14
+      Classifier cls;   // 16 fields; the bracket itself is tiled by fields 1..14 (make_classifier with a fast division)
+      cls.scale = __fdividef(13.0f, hi - lo);
+      cls.bias23 = fmaf(-lo, cls.scale, 1.0f) + 8388608.0f;
       const bool fast = finite && lo < hi && isfinite(cls.scale) && isfinite(cls.bias23);
       slow = !fast;
       if (fast) {
@@ -579,7 +585,7 @@ __device__ __forceinline__ bool lazy_probs(const AcceptParams& P, int b, int nod
       thr = select_slow<NE>(tmp, k, fmn, fmx, sm);
       __syncthreads();
     }
-    const float z_obs = (thr - mean) / sd;
+    const float z_obs = __fdividef(thr - mean, sd);
     if (isfinite(z_obs)) { z_run = z_obs; win_run = P.win_sd; }   // a walk visits too few rows to adapt the width
   }
   TR(43);
